@@ -1,0 +1,299 @@
+// DINOv3 ViT encoder forward on sm_100a: preprocess -> patch-embed GEMM -> L x (LN, QKV GEMM, attention with
+// RoPE prologue, proj GEMM + residual, LN, up GEMM + GELU, down GEMM + residual) -> final LN on the CLS rows.
+// Reference path: cbas.py:672-677 DinoEncoder.forward -> transformers DINOv3ViTModel.forward
+// (modeling_dinov3_vit.py:530-555).  Residual stream is fp32; GEMM operands are bf16 with fp32 accumulation.
+#include "../../include/cbas_b200.h"
+#include "attention.cuh"
+#include "common.h"
+#include "gemm_tcgen05.cuh"
+#include "layernorm.cuh"
+#include "preprocess.cuh"
+
+#include <vector>
+
+using namespace cbas;
+
+namespace {
+
+// float planes [n,H,W] in [0,1] (DinoEncoder.__call__ input, cbas.py:435) -> folded-K patch matrix (x*255 as bf16)
+__global__ void __launch_bounds__(256)
+preprocess_plane_kernel(const float* __restrict__ planes, __nv_bfloat16* __restrict__ A, int n_frames, int H, int W) {
+    const int nw = W >> 4, nh = H >> 4;
+    const long long total = (long long)n_frames * H * nw;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int px = gid % nw;
+    const long long t = gid / nw;
+    const int y = t % H;
+    const int f = t / H;
+    const float4* src = reinterpret_cast<const float4*>(planes + ((long long)f * H + y) * W + px * 16);
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldg(src + i);
+        o[2 * i] = pack_bf16(v.x * 255.0f, v.y * 255.0f);
+        o[2 * i + 1] = pack_bf16(v.z * 255.0f, v.w * 255.0f);
+    }
+    __nv_bfloat16* dst = A + ((long long)f * nh * nw + (long long)(y >> 4) * nw + px) * 256 + (y & 15) * 16;
+    reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+template <typename OutT>
+int launch_layernorm(const float* in, long long in_row_stride, const float* g, const float* b, OutT* out, int rows,
+                     int D, float eps, cudaStream_t s) {
+    if (rows <= 0) return 0;
+    const int threads = 256, rows_per_block = threads / 32;
+    const int grid = (rows + rows_per_block - 1) / rows_per_block;
+    switch (D) {
+        case 384: layernorm_kernel<384, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps); break;
+        case 768: layernorm_kernel<768, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps); break;
+        case 1024: layernorm_kernel<1024, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps); break;
+        case 128: layernorm_kernel<128, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps); break;
+        case 256: layernorm_kernel<256, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps); break;
+        default: return fail("LayerNorm width " + std::to_string(D) + " not instantiated (384/768/1024)");
+    }
+    count_launch();
+    return check_cuda(cudaGetLastError(), "layernorm_kernel launch");
+}
+
+int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* cs, const float* sn, int frames,
+                     int T, int prefix, int heads, cudaStream_t s) {
+    if (frames <= 0) return 0;
+    const int TP = (T + 15) & ~15;
+    const int smem = 3 * TP * 128;
+    static int configured_smem = 0;
+    if (smem > configured_smem) {
+        CBAS_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured_smem = smem;
+    }
+    const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
+    attention_kernel<<<frames * heads, ATT_THREADS, smem, s>>>(qkv, out, cs, sn, T, prefix, heads, heads * ATT_HEAD_DIM,
+                                                               scale_log2);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "attention_kernel launch");
+}
+
+int launch_preprocess_green(const uint8_t* frames, __nv_bfloat16* A, int n, int H, int W, long long fs, int rs,
+                            cudaStream_t s) {
+    if (n <= 0) return 0;
+    if (H % 16 || W % 16) return fail("frame size must be a multiple of the 16-pixel patch");
+    const long long total = (long long)n * H * (W / 16);
+    preprocess_green_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(frames, A, n, H, W, fs, rs);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "preprocess_green_kernel launch");
+}
+
+int launch_preprocess_resize(const uint8_t* frames, __nv_bfloat16* A, int n, int H, int W, long long fs, int rs,
+                             int side, const ResizeTaps& tp, cudaStream_t s) {
+    if (n <= 0) return 0;
+    if (side % 16) return fail("resize target must be a multiple of the 16-pixel patch");
+    if (tp.taps_x > RESIZE_MAX_TAPS * 4 || tp.taps_y > RESIZE_MAX_TAPS * 4) return fail("too many resize taps");
+    const long long total = (long long)n * side * (side / 8);
+    // ImageNet mean/std (transformers image_utils.IMAGENET_DEFAULT_MEAN / _STD)
+    const float3 mean = make_float3(0.485f, 0.456f, 0.406f);
+    const float3 istd = make_float3(1.0f / 0.229f, 1.0f / 0.224f, 1.0f / 0.225f);
+    preprocess_resize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(frames, A, n, H, W, fs, rs, side, tp, mean,
+                                                                            istd);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "preprocess_resize_kernel launch");
+}
+
+}  // namespace
+
+struct cbas_encoder {
+    cbas_encoder_cfg cfg;
+    cbas_encoder_weights w;
+    std::vector<cbas_layer_weights> layers;
+    int T = 0, Np = 0, Kp = 0;
+    // workspace (device)
+    __nv_bfloat16* a_patch = nullptr;  // [max*Np, Kp]
+    float* h = nullptr;                // [max*T, D]   residual stream
+    __nv_bfloat16* xn = nullptr;       // [max*T, D]   LN output / attention output
+    __nv_bfloat16* qkv = nullptr;      // [max*T, 3D]
+    __nv_bfloat16* u = nullptr;        // [max*T, I]
+};
+
+namespace {
+
+int encoder_embed(cbas_encoder* e, const uint8_t* frames_u8, const float* planes, int n, long long fs, int rs,
+                  cudaStream_t s) {
+    const cbas_encoder_cfg& c = e->cfg;
+    if (planes) {
+        if (c.mode != CBAS_PRE_REFERENCE) return fail("float-plane input is only defined for REFERENCE preprocessing");
+        const long long total = (long long)n * c.in_h * (c.in_w / 16);
+        preprocess_plane_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(planes, e->a_patch, n, c.in_h, c.in_w);
+        count_launch();
+        if (int rc = check_cuda(cudaGetLastError(), "preprocess_plane_kernel launch")) return rc;
+    } else if (c.mode == CBAS_PRE_REFERENCE) {
+        if (int rc = launch_preprocess_green(frames_u8, e->a_patch, n, c.in_h, c.in_w, fs, rs, s)) return rc;
+    } else {
+        ResizeTaps tp{(const int*)e->w.rs_ymin, (const float*)e->w.rs_wy, (const int*)e->w.rs_xmin,
+                      (const float*)e->w.rs_wx, c.resize_taps_y, c.resize_taps_x};
+        if (int rc = launch_preprocess_resize(frames_u8, e->a_patch, n, c.in_h, c.in_w, fs, rs, c.side, tp, s)) return rc;
+    }
+    const int D = c.hidden;
+    {
+        const long long total = (long long)n * c.prefix_tokens * (D / 4);
+        fill_prefix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(e->h, (const float*)e->w.prefix, n, e->T,
+                                                                          c.prefix_tokens, D);
+        count_launch();
+        if (int rc = check_cuda(cudaGetLastError(), "fill_prefix_kernel launch")) return rc;
+    }
+    GemmParams p{};
+    p.M = n * e->Np; p.N = D; p.K = e->Kp;
+    p.bias = (const float*)e->w.b_patch;
+    p.out = e->h; p.ldo = D;
+    p.rows_in = e->Np; p.rows_out = e->T; p.prefix = c.prefix_tokens;
+    return launch_gemm(e->a_patch, e->Kp, (const __nv_bfloat16*)e->w.w_patch, e->Kp, p, EPI_PATCH_F32, s);
+}
+
+int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
+    const cbas_encoder_cfg& c = e->cfg;
+    const cbas_layer_weights& L = e->layers[li];
+    const int D = c.hidden, I = c.intermediate, M = n * e->T;
+    if (int rc = launch_layernorm<__nv_bfloat16>(e->h, 1, (const float*)L.ln1_g, (const float*)L.ln1_b, e->xn, M, D,
+                                                 c.ln_eps, s)) return rc;
+    GemmParams p{};
+    p.M = M; p.N = 3 * D; p.K = D; p.bias = (const float*)L.b_qkv; p.out = e->qkv; p.ldo = 3 * D;
+    if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16, s)) return rc;
+    if (int rc = launch_attention(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n, e->T,
+                                  c.prefix_tokens, c.heads, s)) return rc;
+    p = GemmParams{};
+    p.M = M; p.N = D; p.K = D; p.bias = (const float*)L.b_o; p.out = e->h; p.ldo = D;
+    if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_o, D, p, EPI_RESID_F32, s)) return rc;
+    if (int rc = launch_layernorm<__nv_bfloat16>(e->h, 1, (const float*)L.ln2_g, (const float*)L.ln2_b, e->xn, M, D,
+                                                 c.ln_eps, s)) return rc;
+    p = GemmParams{};
+    p.M = M; p.N = I; p.K = D; p.bias = (const float*)L.b_up; p.out = e->u; p.ldo = I;
+    if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_up, D, p, EPI_BIAS_GELU_BF16, s)) return rc;
+    p = GemmParams{};
+    p.M = M; p.N = D; p.K = I; p.bias = (const float*)L.b_down; p.out = e->h; p.ldo = D;
+    return launch_gemm(e->u, I, (const __nv_bfloat16*)L.w_down, I, p, EPI_RESID_F32, s);
+}
+
+int encoder_forward(cbas_encoder* e, const uint8_t* frames_u8, const float* planes, int n, long long fs, int rs,
+                    int stop_after_layer, float* hidden_out, float* emb_out, cudaStream_t s) {
+    if (!e) return fail("null encoder");
+    if (n < 0 || n > e->cfg.max_frames) return fail("n exceeds the encoder's max_frames");
+    if (n == 0) return 0;
+    if (int rc = encoder_embed(e, frames_u8, planes, n, fs, rs, s)) return rc;
+    const int L = stop_after_layer >= 0 ? stop_after_layer : e->cfg.layers;
+    for (int li = 0; li < L; ++li)
+        if (int rc = encoder_layer(e, li, n, s)) return rc;
+    const int D = e->cfg.hidden;
+    if (hidden_out)
+        CBAS_CHECK(cudaMemcpyAsync(hidden_out, e->h, (size_t)n * e->T * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (emb_out) {
+        // final norm on the CLS row of every frame only (rows frame*T): modeling_dinov3_vit.py:547-548, cbas.py:677
+        if (int rc = launch_layernorm<float>(e->h, e->T, (const float*)e->w.lnf_g, (const float*)e->w.lnf_b, emb_out,
+                                             n, D, e->cfg.ln_eps, s)) return rc;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cbas_b200_encoder_create(const cbas_encoder_cfg* cfg, const cbas_encoder_weights* w, cbas_encoder** out) {
+    if (!cfg || !w || !out) return fail("null argument");
+    if (cfg->hidden % 128 || cfg->hidden != cfg->heads * ATT_HEAD_DIM)
+        return fail("hidden must be heads*64 and a multiple of 128");
+    if (cfg->hidden != 384 && cfg->hidden != 768 && cfg->hidden != 1024)
+        return fail("hidden size must be 384, 768 or 1024 (DINOv3 ViT-S/B/L)");
+    if (cfg->intermediate % 128) return fail("intermediate size must be a multiple of 128");
+    if (cfg->side % 16 || cfg->side <= 0) return fail("ViT input side must be a positive multiple of 16");
+    if (cfg->mode == CBAS_PRE_REFERENCE && (cfg->in_h != cfg->side || cfg->in_w != cfg->side))
+        return fail("REFERENCE preprocessing keeps the native (square) resolution: in_h == in_w == side");
+    if (cfg->mode != CBAS_PRE_REFERENCE && cfg->mode != CBAS_PRE_PROCESSOR) return fail("unknown preprocessing mode");
+    if (cfg->max_frames <= 0) return fail("max_frames must be positive");
+    auto* e = new cbas_encoder();
+    e->cfg = *cfg;
+    e->w = *w;
+    e->layers.assign(w->layers, w->layers + cfg->layers);
+    e->w.layers = e->layers.data();
+    const int ns = cfg->side / 16;
+    e->Np = ns * ns;
+    e->T = e->Np + cfg->prefix_tokens;
+    e->Kp = cfg->mode == CBAS_PRE_REFERENCE ? 256 : 768;
+    const size_t mt = (size_t)cfg->max_frames * e->T, D = cfg->hidden;
+    cudaError_t err = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) { if (err == cudaSuccess) err = cudaMalloc(p, bytes); };
+    alloc((void**)&e->a_patch, (size_t)cfg->max_frames * e->Np * e->Kp * 2);
+    alloc((void**)&e->h, mt * D * 4);
+    alloc((void**)&e->xn, mt * D * 2);
+    alloc((void**)&e->qkv, mt * 3 * D * 2);
+    alloc((void**)&e->u, mt * (size_t)cfg->intermediate * 2);
+    if (err != cudaSuccess) {
+        cbas_b200_encoder_destroy(e);
+        return check_cuda(err, "encoder workspace cudaMalloc");
+    }
+    *out = e;
+    return 0;
+}
+
+void cbas_b200_encoder_destroy(cbas_encoder* e) {
+    if (!e) return;
+    cudaFree(e->a_patch); cudaFree(e->h); cudaFree(e->xn); cudaFree(e->qkv); cudaFree(e->u);
+    delete e;
+}
+
+int cbas_b200_encoder_forward_u8(cbas_encoder* enc, const uint8_t* frames_dev, int32_t n, int64_t frame_stride,
+                                 int32_t row_stride, float* emb_out_dev, void* stream) {
+    return encoder_forward(enc, frames_dev, nullptr, n, frame_stride, row_stride, -1, nullptr, emb_out_dev,
+                           (cudaStream_t)stream);
+}
+
+int cbas_b200_encoder_forward_f32(cbas_encoder* enc, const float* planes_dev, int32_t n, float* emb_out_dev,
+                                  void* stream) {
+    return encoder_forward(enc, nullptr, planes_dev, n, 0, 0, -1, nullptr, emb_out_dev, (cudaStream_t)stream);
+}
+
+int cbas_b200_encoder_debug_hidden(cbas_encoder* enc, const uint8_t* frames_dev, int32_t n, int64_t frame_stride,
+                                   int32_t row_stride, int32_t after_layer, float* hidden_out_dev, void* stream) {
+    if (!enc) return fail("null encoder");
+    if (after_layer < 0 || after_layer > enc->cfg.layers) return fail("after_layer out of range");
+    return encoder_forward(enc, frames_dev, nullptr, n, frame_stride, row_stride, after_layer, hidden_out_dev, nullptr,
+                           (cudaStream_t)stream);
+}
+
+int cbas_b200_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_dev, void* out_dev, int32_t M,
+                        int32_t N, int32_t K, int32_t epi, void* stream) {
+    if (epi == EPI_PATCH_F32) return fail("the patch epilogue is internal to the encoder");
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.bias = bias_dev; p.out = out_dev; p.ldo = N;
+    return launch_gemm((const __nv_bfloat16*)a_dev, K, (const __nv_bfloat16*)w_dev, K, p, epi, (cudaStream_t)stream);
+}
+
+int cbas_b200_layernorm(const float* in_dev, const float* gamma_dev, const float* beta_dev, void* out_bf16_dev,
+                        int32_t rows, int32_t D, float eps, void* stream) {
+    return launch_layernorm<__nv_bfloat16>(in_dev, 1, gamma_dev, beta_dev, (__nv_bfloat16*)out_bf16_dev, rows, D, eps,
+                                           (cudaStream_t)stream);
+}
+
+int cbas_b200_attention(const void* qkv_bf16_dev, void* out_bf16_dev, const float* rope_cos_dev,
+                        const float* rope_sin_dev, int32_t frames, int32_t T, int32_t prefix, int32_t heads,
+                        void* stream) {
+    if (T <= 0 || T > 1024) return fail("attention: tokens per frame must be in [1, 1024]");
+    if (3 * ((T + 15) & ~15) * 128 > 227 * 1024) return fail("attention: frame does not fit in shared memory");
+    return launch_attention((const __nv_bfloat16*)qkv_bf16_dev, (__nv_bfloat16*)out_bf16_dev, rope_cos_dev,
+                            rope_sin_dev, frames, T, prefix, heads, (cudaStream_t)stream);
+}
+
+int cbas_b200_preprocess_green(const uint8_t* frames_dev, void* a_bf16_dev, int32_t n, int32_t H, int32_t W,
+                               int64_t frame_stride, int32_t row_stride, void* stream) {
+    return launch_preprocess_green(frames_dev, (__nv_bfloat16*)a_bf16_dev, n, H, W, frame_stride, row_stride,
+                                   (cudaStream_t)stream);
+}
+
+int cbas_b200_preprocess_resize(const uint8_t* frames_dev, void* a_bf16_dev, int32_t n, int32_t H, int32_t W,
+                                int64_t frame_stride, int32_t row_stride, int32_t side, const int32_t* ymin_dev,
+                                const float* wy_dev, int32_t taps_y, const int32_t* xmin_dev, const float* wx_dev,
+                                int32_t taps_x, void* stream) {
+    ResizeTaps tp{ymin_dev, wy_dev, xmin_dev, wx_dev, taps_y, taps_x};
+    return launch_preprocess_resize(frames_dev, (__nv_bfloat16*)a_bf16_dev, n, H, W, frame_stride, row_stride, side,
+                                    tp, (cudaStream_t)stream);
+}
+
+}  // extern "C"

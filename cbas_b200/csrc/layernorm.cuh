@@ -1,0 +1,57 @@
+// Row LayerNorm over the fp32 residual stream (HF modeling_dinov3_vit.py:411,416,433,445,520,547;
+// nn.LayerNorm(D, eps=1e-5)).  One warp per row, the row held in registers, two-pass fp32 statistics
+// (mean, then variance of the centred values - same arithmetic as ATen), 16-byte loads, bf16 or fp32 out.
+// HBM-bound: reads D*4 B and writes D*2 B per row.
+#pragma once
+#include "ptx.cuh"
+
+namespace cbas {
+
+// in:  fp32 rows, row r at in + (r * in_row_stride) * D      (in_row_stride lets the final LN visit CLS rows only)
+// out: OutT rows, contiguous [rows, D]
+template <int D, typename OutT>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ in, long long in_row_stride, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, OutT* __restrict__ out, int rows, float eps) {
+    static_assert(D % 128 == 0, "D must be a multiple of 128");
+    constexpr int V = D / 128;  // float4 per lane
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float4* src = reinterpret_cast<const float4*>(in + (long long)warp * in_row_stride * D);
+    float4 x[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) x[i] = src[lane + 32 * i];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        x[i].x -= mean; x[i].y -= mean; x[i].z -= mean; x[i].w -= mean;
+        q += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const float4 g = __ldg(g4 + lane + 32 * i), b = __ldg(b4 + lane + 32 * i);
+        float4 y;
+        y.x = x[i].x * rstd * g.x + b.x;
+        y.y = x[i].y * rstd * g.y + b.y;
+        y.z = x[i].z * rstd * g.z + b.z;
+        y.w = x[i].w * rstd * g.w + b.w;
+        if constexpr (sizeof(OutT) == 2) {
+            uint2 o;
+            o.x = pack_bf16(y.x, y.y);
+            o.y = pack_bf16(y.z, y.w);
+            reinterpret_cast<uint2*>(out + (long long)warp * D)[lane + 32 * i] = o;
+        } else {
+            reinterpret_cast<float4*>(out + (long long)warp * D)[lane + 32 * i] = y;
+        }
+    }
+}
+
+}  // namespace cbas

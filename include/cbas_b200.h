@@ -1,0 +1,157 @@
+/* cbas_b200 - C ABI of the B200-native CBAS hot path (libcbas_b200.so).
+ *
+ * The reference (jones-lab-tamu/CBAS) has no FFI: its seam is Python.  Each entry point below names the
+ * reference Python symbol (file:line under the reference checkout) whose GPU work it replaces; the Python
+ * mirror in cbas_b200/ keeps those symbols' signatures and binds this library with ctypes.
+ *
+ * Conventions: plain pointers and sizes only; every *_dev pointer is a CUDA device pointer in the calling
+ * process' primary context; `stream` is a cudaStream_t passed as void* (PyTorch: torch.cuda.current_stream()
+ * .cuda_stream); calls are asynchronous on that stream unless stated.  Every function returns 0 on success,
+ * non-zero on failure; cbas_b200_last_error() returns a thread-local message for the last failure.
+ * The library is re-entrant across host threads as long as two threads do not share one Encoder/Head handle
+ * (workthreads.py:272,370 - one EncodeThread and one ClassificationThread, each on its own CUDA stream).
+ */
+#ifndef CBAS_B200_H
+#define CBAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBAS_B200_ABI_VERSION 1
+
+/* preprocessing modes (SURVEY.md 8a rows P / P') */
+#define CBAS_PRE_REFERENCE 0 /* cbas.py:431 + cbas.py:672-675: green/255 replicated x3, native resolution   */
+#define CBAS_PRE_PROCESSOR 1 /* HF image_processing_dinov3_vit.py:45-86: rescale, AA-bilinear resize, normalise */
+
+const char* cbas_b200_last_error(void);
+int cbas_b200_abi_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+unsigned long long cbas_b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------ encoder
+ * Replaces DinoEncoder.forward (cbas.py:672-677) = preprocessing + transformers DINOv3ViTModel.forward
+ * (modeling_dinov3_vit.py:530-555) + CLS pooling.  Weights are device pointers prepared once by the host
+ * mirror (cbas_b200/encoder.py) from the HF state_dict; the library keeps the pointers, not copies. */
+typedef struct {
+    int32_t hidden;        /* D: 384 / 768 / 1024 (multiple of 128)                                   */
+    int32_t layers;        /* L                                                                       */
+    int32_t heads;         /* D / 64 (head_dim must be 64)                                            */
+    int32_t intermediate;  /* I                                                                       */
+    int32_t prefix_tokens; /* 1 CLS + num_register_tokens                                             */
+    int32_t mode;          /* CBAS_PRE_*                                                              */
+    int32_t in_h, in_w;    /* source frame size                                                       */
+    int32_t side;          /* ViT input side in pixels: in_h (= in_w) for REFERENCE, resize target for PROCESSOR */
+    int32_t max_frames;    /* largest n a forward call may pass (workspace is sized for it)           */
+    float ln_eps;
+    int32_t resize_taps_y, resize_taps_x; /* PROCESSOR only */
+} cbas_encoder_cfg;
+
+typedef struct {
+    const void* ln1_g; const void* ln1_b;     /* f32 [D]                                               */
+    const void* w_qkv; const void* b_qkv;     /* bf16 [3D,D] (q|k|v rows), f32 [3D] (k part zero)      */
+    const void* w_o;   const void* b_o;       /* bf16 [D,D], f32 [D]   - LayerScale lambda1 folded in  */
+    const void* ln2_g; const void* ln2_b;     /* f32 [D]                                               */
+    const void* w_up;  const void* b_up;      /* bf16 [I,D], f32 [I]                                   */
+    const void* w_down; const void* b_down;   /* bf16 [D,I], f32 [D]   - LayerScale lambda2 folded in  */
+} cbas_layer_weights;
+
+typedef struct {
+    const void* w_patch; const void* b_patch; /* bf16 [D,Kp] (Kp = 256 REFERENCE-folded, 768 PROCESSOR), f32 [D] */
+    const void* prefix;                       /* f32 [prefix_tokens, D]: cls_token then register_tokens */
+    const void* rope_cos; const void* rope_sin; /* f32 [(side/16)^2, 32]                                */
+    const void* lnf_g; const void* lnf_b;     /* f32 [D] final norm                                    */
+    const cbas_layer_weights* layers;         /* host array [L]                                        */
+    /* PROCESSOR mode resize taps (device): first source index + normalised weights per output coordinate */
+    const void* rs_ymin; const void* rs_wy; const void* rs_xmin; const void* rs_wx;
+} cbas_encoder_weights;
+
+typedef struct cbas_encoder cbas_encoder;
+
+int cbas_b200_encoder_create(const cbas_encoder_cfg* cfg, const cbas_encoder_weights* w, cbas_encoder** out);
+void cbas_b200_encoder_destroy(cbas_encoder* enc);
+
+/* frames_dev: uint8 RGB HWC (what decord's get_batch(...).asnumpy() yields, cbas.py:425), n frames,
+ * frame_stride / row_stride in bytes.  emb_out_dev: f32 [n, D] pooled CLS embedding after the final norm. */
+int cbas_b200_encoder_forward_u8(cbas_encoder* enc, const uint8_t* frames_dev, int32_t n, int64_t frame_stride,
+                                 int32_t row_stride, float* emb_out_dev, void* stream);
+/* DinoEncoder.__call__ compatibility (cbas.py:435,672): planes_dev f32 [n, in_h, in_w] in [0,1] (REFERENCE only). */
+int cbas_b200_encoder_forward_f32(cbas_encoder* enc, const float* planes_dev, int32_t n, float* emb_out_dev,
+                                  void* stream);
+/* Debug/test taps: copy of the residual stream f32 [n*T, D] after `after_layer` blocks (0 = after embeddings). */
+int cbas_b200_encoder_debug_hidden(cbas_encoder* enc, const uint8_t* frames_dev, int32_t n, int64_t frame_stride,
+                                   int32_t row_stride, int32_t after_layer, float* hidden_out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------- kernel-level entry points
+ * (used by the parity tests and by bench.py's roofline leg; same kernels the encoder launches) */
+/* out = epilogue(A[M,K] * W[N,K]^T + bias); epi: 0 bias->bf16, 1 bias+GELU(erf)->bf16, 2 f32 out += , 4 bias->f32 */
+int cbas_b200_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_dev, void* out_dev, int32_t M,
+                        int32_t N, int32_t K, int32_t epi, void* stream);
+int cbas_b200_layernorm(const float* in_dev, const float* gamma_dev, const float* beta_dev, void* out_bf16_dev,
+                        int32_t rows, int32_t D, float eps, void* stream);
+int cbas_b200_attention(const void* qkv_bf16_dev, void* out_bf16_dev, const float* rope_cos_dev,
+                        const float* rope_sin_dev, int32_t frames, int32_t T, int32_t prefix, int32_t heads,
+                        void* stream);
+int cbas_b200_preprocess_green(const uint8_t* frames_dev, void* a_bf16_dev, int32_t n, int32_t H, int32_t W,
+                               int64_t frame_stride, int32_t row_stride, void* stream);
+int cbas_b200_preprocess_resize(const uint8_t* frames_dev, void* a_bf16_dev, int32_t n, int32_t H, int32_t W,
+                                int64_t frame_stride, int32_t row_stride, int32_t side, const int32_t* ymin_dev,
+                                const float* wy_dev, int32_t taps_y, const int32_t* xmin_dev, const float* wx_dev,
+                                int32_t taps_x, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ head
+ * Replaces ClassifierLSTMDeltas.forward (classifier_head.py:150-172) driven by infer_file's window loop
+ * (cbas.py:497-551): for every frame f the window [f-seq_len/2, f+seq_len/2] with replicate padding at the
+ * ends of the video, then softmax(logits / max(1e-3, temperature)).  All weights f32 device pointers in the
+ * reference state_dict layout (workthreads.py:856 model.pth keys). */
+typedef struct {
+    int32_t in_features;   /* F (768)                    */
+    int32_t out_features;  /* C (number of behaviours)   */
+    int32_t seq_len;       /* odd window length (31)     */
+    int32_t bottleneck;    /* 128                        */
+    int32_t lstm_hidden;   /* 64                         */
+    int32_t center_window; /* sw = 5                     */
+    float ema_alpha;       /* 0.3                        */
+    int32_t use_acceleration; /* must be 1               */
+    int32_t lstm_layers;      /* must be 1               */
+} cbas_head_cfg;
+
+typedef struct {
+    const float* cls_w; const float* cls_b;       /* [128,F], [128] cls_bottleneck.0   */
+    const float* delta_w; const float* delta_b;   /* delta_bottleneck.0                */
+    const float* acc_w; const float* acc_b;       /* acc_bottleneck.0                  */
+    const float* cls_ln_g; const float* cls_ln_b; /* [128]                             */
+    const float* delta_ln_g; const float* delta_ln_b;
+    const float* acc_ln_g; const float* acc_ln_b;
+    const float* lin0_w; const float* lin0_b;     /* [256,384], [256]                  */
+    const float* lin1_w; const float* lin1_b;     /* [C,F], [C]                        */
+    const float* lin2_w; const float* lin2_b;     /* [C,2Hs], [C]                      */
+    const float* att_w; const float* att_b;       /* [1,2Hs], [1]                      */
+    const float* w_ih_f; const float* w_hh_f; const float* b_ih_f; const float* b_hh_f; /* lstm.*_l0         */
+    const float* w_ih_r; const float* w_hh_r; const float* b_ih_r; const float* b_hh_r; /* lstm.*_l0_reverse */
+    float gate;            /* raw parameter (sigmoid applied inside) */
+    float attention_temp;  /* raw parameter (softplus applied inside) */
+} cbas_head_weights;
+
+typedef struct cbas_head cbas_head;
+
+int cbas_b200_head_create(const cbas_head_cfg* cfg, const cbas_head_weights* w, cbas_head** out);
+void cbas_b200_head_destroy(cbas_head* head);
+/* emb_dev: f16 [n_frames, F] (the `cls` dataset as stored, cbas.py:420) ; probs_out_dev: f32 [n_frames, C].
+ * logits_out_dev (optional, may be null): f32 [n_frames, C] final_logits before temperature/softmax. */
+int cbas_b200_head_infer(cbas_head* head, const void* emb_f16_dev, int64_t n_frames, float temperature,
+                         float* probs_out_dev, float* logits_out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ actogram
+ * Replaces the numeric part of Actogram.__init__ (cbas.py:969-999): per frame
+ * event = (p_b * [max_{b' != b} p_b' < p_b]) >= threshold ; bins[k] = sum of events over bin_frames frames
+ * (last partial bin kept).  probs_dev f32 [n, C]; bins_out_dev int32 [ceil(n / bin_frames)]. */
+int cbas_b200_actogram_bins(const float* probs_dev, int64_t n, int32_t C, int32_t behavior, float threshold,
+                            int64_t bin_frames, int32_t* bins_out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBAS_B200_H */
