@@ -66,6 +66,8 @@ SIGNATURES = {
     "cbas_b200_last_error": (C.c_char_p, []),
     "cbas_b200_abi_version": (C.c_int, []),
     "cbas_b200_launch_count": (C.c_ulonglong, []),
+    "cbas_b200_profile_enable": (C.c_int, [C.c_int]),
+    "cbas_b200_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "cbas_b200_encoder_create": (C.c_int, [C.POINTER(EncoderCfg), C.POINTER(EncoderWeights), C.POINTER(c_void_p)]),
     "cbas_b200_encoder_destroy": (None, [c_void_p]),
     "cbas_b200_encoder_forward_u8": (C.c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
@@ -120,3 +122,23 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib().cbas_b200_launch_count())
+
+
+PROFILE_TAGS = ("preprocess", "patch_gemm", "layernorm", "qkv_gemm", "attention", "proj_gemm", "up_gemm", "down_gemm",
+                "final_ln", "head_split", "head_proj_gemm", "head_features", "head_lin0_gemm", "head_center",
+                "head_ih_gemm", "head_lstm", "actogram", "other")
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().cbas_b200_profile_enable(1 if on else 0), "profile_enable")
+
+
+def profile_read() -> dict:
+    """{tag: (total_ms, launches)} for every tag that recorded at least one launch."""
+    out = {}
+    for i, name in enumerate(PROFILE_TAGS):
+        ms, n = C.c_double(), C.c_longlong()
+        check(lib().cbas_b200_profile_read(i, C.byref(ms), C.byref(n)), "profile_read")
+        if n.value:
+            out[name] = (ms.value, n.value)
+    return out

@@ -16,10 +16,23 @@ int check_cuda(cudaError_t e, const char* what);  // 0 if cudaSuccess, else reco
 void count_launch(int n = 1);
 int sm_count();
 
+// Optional per-kernel timing (cbas_b200_profile_*): CUDA events recorded on the launch stream around a launch.
+enum ProfTag : int {
+    PROF_PREPROCESS = 0, PROF_PATCH_GEMM, PROF_LAYERNORM, PROF_QKV_GEMM, PROF_ATTENTION, PROF_PROJ_GEMM, PROF_UP_GEMM,
+    PROF_DOWN_GEMM, PROF_FINAL_LN, PROF_HEAD_SPLIT, PROF_HEAD_PROJ_GEMM, PROF_HEAD_FEATURES, PROF_HEAD_LIN0_GEMM,
+    PROF_HEAD_CENTER, PROF_HEAD_IH_GEMM, PROF_HEAD_LSTM, PROF_ACTOGRAM, PROF_OTHER, PROF_NUM_TAGS
+};
+struct ProfScope {
+    ProfScope(int tag, cudaStream_t s);
+    ~ProfScope();
+    int slot;
+    cudaStream_t stream;
+};
+
 struct GemmParams;
 // C[M,N] = A[M,K] W[N,K]^T with one of the GemmEpilogue modes; lda/ldw in elements.
 int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, const GemmParams& p, int epi,
-                cudaStream_t stream);
+                cudaStream_t stream, int prof_tag = PROF_OTHER);
 
 #define CBAS_CHECK(expr)                                   \
     do {                                                   \

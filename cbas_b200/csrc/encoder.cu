@@ -41,8 +41,9 @@ preprocess_plane_kernel(const float* __restrict__ planes, __nv_bfloat16* __restr
 
 template <typename OutT>
 int launch_layernorm(const float* in, long long in_row_stride, const float* g, const float* b, OutT* out, int rows,
-                     int D, float eps, cudaStream_t s) {
+                     int D, float eps, cudaStream_t s, int tag = PROF_LAYERNORM) {
     if (rows <= 0) return 0;
+    ProfScope prof(tag, s);
     const int threads = 256, rows_per_block = threads / 32;
     const int grid = (rows + rows_per_block - 1) / rows_per_block;
     switch (D) {
@@ -60,6 +61,7 @@ int launch_layernorm(const float* in, long long in_row_stride, const float* g, c
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* cs, const float* sn, int frames,
                      int T, int prefix, int heads, cudaStream_t s) {
     if (frames <= 0) return 0;
+    ProfScope prof(PROF_ATTENTION, s);
     const int TP = (T + 15) & ~15;
     const int smem = 3 * TP * 128;
     static int configured_smem = 0;
@@ -78,6 +80,7 @@ int launch_preprocess_green(const uint8_t* frames, __nv_bfloat16* A, int n, int 
                             cudaStream_t s) {
     if (n <= 0) return 0;
     if (H % 16 || W % 16) return fail("frame size must be a multiple of the 16-pixel patch");
+    ProfScope prof(PROF_PREPROCESS, s);
     const long long total = (long long)n * H * (W / 16);
     preprocess_green_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(frames, A, n, H, W, fs, rs);
     count_launch();
@@ -89,6 +92,7 @@ int launch_preprocess_resize(const uint8_t* frames, __nv_bfloat16* A, int n, int
     if (n <= 0) return 0;
     if (side % 16) return fail("resize target must be a multiple of the 16-pixel patch");
     if (tp.taps_x > RESIZE_MAX_TAPS * 4 || tp.taps_y > RESIZE_MAX_TAPS * 4) return fail("too many resize taps");
+    ProfScope prof(PROF_PREPROCESS, s);
     const long long total = (long long)n * side * (side / 8);
     // ImageNet mean/std (transformers image_utils.IMAGENET_DEFAULT_MEAN / _STD)
     const float3 mean = make_float3(0.485f, 0.456f, 0.406f);
@@ -145,7 +149,8 @@ int encoder_embed(cbas_encoder* e, const uint8_t* frames_u8, const float* planes
     p.bias = (const float*)e->w.b_patch;
     p.out = e->h; p.ldo = D;
     p.rows_in = e->Np; p.rows_out = e->T; p.prefix = c.prefix_tokens;
-    return launch_gemm(e->a_patch, e->Kp, (const __nv_bfloat16*)e->w.w_patch, e->Kp, p, EPI_PATCH_F32, s);
+    return launch_gemm(e->a_patch, e->Kp, (const __nv_bfloat16*)e->w.w_patch, e->Kp, p, EPI_PATCH_F32, s,
+                       PROF_PATCH_GEMM);
 }
 
 int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
@@ -156,20 +161,20 @@ int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
                                                  c.ln_eps, s)) return rc;
     GemmParams p{};
     p.M = M; p.N = 3 * D; p.K = D; p.bias = (const float*)L.b_qkv; p.out = e->qkv; p.ldo = 3 * D;
-    if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16, s)) return rc;
+    if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16, s, PROF_QKV_GEMM)) return rc;
     if (int rc = launch_attention(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n, e->T,
                                   c.prefix_tokens, c.heads, s)) return rc;
     p = GemmParams{};
     p.M = M; p.N = D; p.K = D; p.bias = (const float*)L.b_o; p.out = e->h; p.ldo = D;
-    if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_o, D, p, EPI_RESID_F32, s)) return rc;
+    if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_o, D, p, EPI_RESID_F32, s, PROF_PROJ_GEMM)) return rc;
     if (int rc = launch_layernorm<__nv_bfloat16>(e->h, 1, (const float*)L.ln2_g, (const float*)L.ln2_b, e->xn, M, D,
                                                  c.ln_eps, s)) return rc;
     p = GemmParams{};
     p.M = M; p.N = I; p.K = D; p.bias = (const float*)L.b_up; p.out = e->u; p.ldo = I;
-    if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_up, D, p, EPI_BIAS_GELU_BF16, s)) return rc;
+    if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_up, D, p, EPI_BIAS_GELU_BF16, s, PROF_UP_GEMM)) return rc;
     p = GemmParams{};
     p.M = M; p.N = D; p.K = I; p.bias = (const float*)L.b_down; p.out = e->h; p.ldo = D;
-    return launch_gemm(e->u, I, (const __nv_bfloat16*)L.w_down, I, p, EPI_RESID_F32, s);
+    return launch_gemm(e->u, I, (const __nv_bfloat16*)L.w_down, I, p, EPI_RESID_F32, s, PROF_DOWN_GEMM);
 }
 
 int encoder_forward(cbas_encoder* e, const uint8_t* frames_u8, const float* planes, int n, long long fs, int rs,
@@ -187,7 +192,7 @@ int encoder_forward(cbas_encoder* e, const uint8_t* frames_u8, const float* plan
     if (emb_out) {
         // final norm on the CLS row of every frame only (rows frame*T): modeling_dinov3_vit.py:547-548, cbas.py:677
         if (int rc = launch_layernorm<float>(e->h, e->T, (const float*)e->w.lnf_g, (const float*)e->w.lnf_b, emb_out,
-                                             n, D, e->cfg.ln_eps, s)) return rc;
+                                             n, D, e->cfg.ln_eps, s, PROF_FINAL_LN)) return rc;
     }
     return 0;
 }

@@ -79,8 +79,9 @@ int launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
 }  // namespace
 
 int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, const GemmParams& p, int epi,
-                cudaStream_t stream) {
+                cudaStream_t stream, int prof_tag) {
     if (p.M <= 0) return 0;
+    ProfScope prof(prof_tag, stream);
     if (p.K % GEMM_BLOCK_K != 0 || p.K <= 0) return fail("GEMM K must be a positive multiple of 64");
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) || (lda % 8) || (ldw % 8))
         return fail("GEMM operands must be 16-byte aligned with row pitch a multiple of 8 elements");

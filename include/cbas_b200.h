@@ -31,6 +31,13 @@ int cbas_b200_abi_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 unsigned long long cbas_b200_launch_count(void);
 
+/* Per-kernel device timing for bench.py's roofline leg: while enabled, every launch is bracketed by CUDA events
+ * on its own stream (tags: 0 preprocess, 1 patch GEMM, 2 LayerNorm, 3 QKV GEMM, 4 attention, 5 proj GEMM,
+ * 6 up GEMM(+GELU), 7 down GEMM, 8 final LN, 9.. head stages, 16 actogram, 17 other).  enable(1) also clears.
+ * profile_read synchronises on the recorded events and returns the summed duration and launch count of a tag. */
+int cbas_b200_profile_enable(int on);
+int cbas_b200_profile_read(int tag, double* total_ms, long long* launches);
+
 /* ------------------------------------------------------------------------------------------------ encoder
  * Replaces DinoEncoder.forward (cbas.py:672-677) = preprocessing + transformers DINOv3ViTModel.forward
  * (modeling_dinov3_vit.py:530-555) + CLS pooling.  Weights are device pointers prepared once by the host

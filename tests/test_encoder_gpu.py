@@ -1,0 +1,87 @@
+"""End-to-end encoder parity: libcbas_b200 vs the fp32 CPU oracle (transformers DINOv3ViTModel wrapped the way
+cbas.py wraps it) on identical synthetic frames and random-init weights, plus the fixture produced by the
+reference's own encode_file.  Gates (BASELINE.json): cosine >= 0.999, max|d|/max|ref| <= 2e-2; also reported:
+mean-centred cosine and per-layer residual-stream error."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from cbas_b200.encoder import DinoEncoder  # noqa: E402
+from oracle import encoder as oenc  # noqa: E402
+from tests.gpu_util import cosine_rows, rel_err  # noqa: E402
+
+
+def _report(tag, got, want):
+    got, want = torch.as_tensor(got).double(), torch.as_tensor(want).double()
+    cos = cosine_rows(got, want).min().item()
+    cc = cosine_rows(got - want.mean(0), want - want.mean(0)).min().item()
+    rel = rel_err(got, want)
+    # input dependence: every GPU row must be nearest to ITS OWN oracle row, not to another frame's
+    dist = torch.cdist(got, want)
+    nn_ok = bool((dist.argmin(dim=1) == torch.arange(len(got))).all())
+    print(f"[parity] {tag}: min cosine {cos:.6f}  mean-centred {cc:.6f}  max|d|/max|ref| {rel:.3e}  nearest-row {nn_ok}")
+    return cos, nn_ok, rel
+
+
+@pytest.mark.parametrize("arch,side,n,scale", [("vits16", 64, 5, 4.0), ("vitb16", 224, 4, 3.0), ("vitb16", 256, 3, 1.0),
+                                              ("vitl16", 96, 3, 2.0)])
+def test_reference_mode_parity(arch, side, n, scale):
+    model = oenc.build_hf_model(arch, seed=0, init_scale=scale)
+    frames = oenc.synthetic_frames(n, side, side, seed=5)
+    want = oenc.encode(model, frames, mode="reference")
+    enc = DinoEncoder.from_hf_model(model, "cuda", max_frames=8)
+    fd = torch.from_numpy(frames).cuda()
+    # per-layer taps first: the first layer that drifts is the one to look at
+    hs = oenc.hidden_states(model, oenc.preprocess_reference(frames))
+    for li in sorted({0, 1, 2, len(hs) - 1}):
+        got = enc.debug_hidden(fd, li).cpu()
+        r = rel_err(got, hs[li])
+        print(f"[parity] {arch}@{side} residual stream after {li} blocks: max|d|/max|ref| {r:.3e}")
+        assert r < 2e-2, f"layer tap {li}"
+    got = enc.encode_u8(fd).cpu()
+    cos, nn_ok, rel = _report(f"{arch}@{side} reference-mode", got, want)
+    assert cos >= 0.999 and rel <= 2e-2
+    assert nn_ok
+    # float-plane entry (DinoEncoder.__call__ contract, cbas.py:435,672)
+    x = torch.from_numpy(frames[:, :, :, 1] / 255.0).float().unsqueeze(1)
+    got2 = enc(x).squeeze(1).cpu()
+    assert got2.shape == (n, model.config.hidden_size)
+    assert rel_err(got2, got) < 1e-5
+
+
+def test_processor_mode_parity():
+    model = oenc.build_hf_model("vitb16", seed=1, init_scale=3.0)
+    frames = oenc.synthetic_frames(4, 256, 256, seed=6)
+    want = oenc.encode(model, frames, mode="processor", size=224)
+    enc = DinoEncoder.from_hf_model(model, "cuda", preprocess="processor", image_size=224, max_frames=8)
+    got = enc.encode_u8(torch.from_numpy(frames).cuda()).cpu()
+    cos, nn_ok, rel = _report("vitb16 processor 256->224", got, want)
+    assert cos >= 0.999 and rel <= 2e-2 and nn_ok
+
+
+def test_against_reference_encode_file_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "encode_file_vitb.npz"))
+    frames = oenc.synthetic_frames(6, 64, 64, seed=int(g["frames_seed"]))
+    model = oenc.build_hf_model("vitb16", seed=int(g["model_seed"]), init_scale=float(g["init_scale"]))
+    enc = DinoEncoder.from_hf_model(model, "cuda", max_frames=8)
+    got = enc.encode_u8(torch.from_numpy(frames).cuda()).cpu()
+    cos, nn_ok, rel = _report("fixture encode_file (reference run)", got, g["cls"].astype(np.float32))
+    assert cos >= 0.999 and rel <= 2e-2 and nn_ok
+
+
+def test_batch_independence_and_chunking():
+    enc = DinoEncoder("synthetic:vits16@3", "cuda", max_frames=4)
+    frames = torch.from_numpy(oenc.synthetic_frames(10, 64, 64, seed=8)).cuda()
+    full = enc.encode_u8(frames)  # 4 + 4 + 2
+    one = torch.cat([enc.encode_u8(frames[i:i + 1]) for i in range(10)])
+    assert torch.equal(full, one)  # same kernels, same tiles per row -> bitwise equal
+
+
+def test_empty_batch():
+    enc = DinoEncoder("synthetic:vits16", "cuda", max_frames=4)
+    out = enc.encode_u8(torch.zeros(0, 64, 64, 3, dtype=torch.uint8, device="cuda"))
+    assert out.shape == (0, 384)

@@ -1,0 +1,59 @@
+"""tcgen05 GEMM against torch.matmul (fp32 reference of the same bf16 operands)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests.gpu_util import gemm, rel_err  # noqa: E402
+
+
+def _mk(M, N, K, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = (torch.randn(M, K, device="cuda", generator=g)).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda", generator=g)
+    return a, w, b
+
+
+@pytest.mark.parametrize("M,N,K", [
+    (128, 128, 64), (128, 256, 64), (128, 256, 128), (300, 256, 256), (657, 768, 768), (1000, 384, 384),
+    (4021, 2304, 768), (2010, 3072, 768), (2010, 768, 3072), (333, 1152, 384), (129, 1024, 4096), (64, 128, 256),
+])
+def test_gemm_bias_f32(M, N, K):
+    a, w, b = _mk(M, N, K)
+    out = gemm(a, w, b, epi=4)
+    want = a.float() @ w.float().T + b
+    torch.cuda.synchronize()
+    e = rel_err(out, want)
+    assert e < 2e-5, f"M{M} N{N} K{K}: rel err {e}; first bad rows {((out-want).abs().amax(1) > 1e-3).nonzero()[:8].flatten().tolist()}"
+
+
+@pytest.mark.parametrize("epi", [0, 1])
+def test_gemm_bf16_epilogues(epi):
+    a, w, b = _mk(777, 768, 768, seed=1)
+    out = gemm(a, w, b, epi=epi).float()
+    want = a.float() @ w.float().T + b
+    if epi == 1:
+        want = torch.nn.functional.gelu(want)
+    assert rel_err(out, want) < 6e-3  # bf16 output rounding (2^-9)
+
+
+def test_gemm_residual_inplace():
+    a, w, b = _mk(515, 768, 3072, seed=2)
+    h = torch.randn(515, 768, device="cuda")
+    want = h + a.float() @ w.float().T + b
+    gemm(a, w, b, epi=2, out=h)
+    assert rel_err(h, want) < 2e-5
+
+
+def test_gemm_no_bias_and_many_tiles():
+    a, w, _ = _mk(128 * 150 + 5, 256, 64, seed=3)  # more tiles than SMs: persistent loop + phase wrap
+    out = gemm(a, w, None, epi=4)
+    want = a.float() @ w.float().T
+    assert rel_err(out, want) < 2e-5
+
+
+def test_gemm_rejects_bad_shapes():
+    a, w, b = _mk(128, 100, 64)
+    with pytest.raises(RuntimeError):
+        gemm(a, w, b, epi=4)

@@ -1,0 +1,98 @@
+"""LayerNorm, fused attention (RoPE prologue) and the preprocess kernels against torch / the oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from cbas_b200 import _lib  # noqa: E402
+from cbas_b200.encoder import aa_bilinear_taps, rope_tables  # noqa: E402
+from oracle import encoder as oenc  # noqa: E402
+from tests.gpu_util import attention, layernorm, rel_err, stream  # noqa: E402
+
+
+@pytest.mark.parametrize("D", [384, 768, 1024])
+def test_layernorm(D):
+    x = torch.randn(1003, D, device="cuda") * 3 + 0.5
+    g = torch.randn(D, device="cuda")
+    b = torch.randn(D, device="cuda")
+    out = layernorm(x, g, b).float()
+    want = F.layer_norm(x, (D,), g, b, 1e-5)
+    assert rel_err(out, want) < 5e-3  # bf16 output
+
+
+def _rope_ref(q, k, cos, sin):
+    # modeling_dinov3_vit.py:203-207,238-268 restated on [B,H,T,64] tensors; cos/sin [Np,32] -> tile(2)
+    cos, sin = torch.cat([cos, cos], -1), torch.cat([sin, sin], -1)
+    P = q.shape[-2] - cos.shape[-2]
+
+    def rot(x):
+        x1, x2 = x[..., :32], x[..., 32:]
+        return torch.cat((-x2, x1), dim=-1)
+
+    def ap(x):
+        xp = x[..., P:, :]
+        return torch.cat([x[..., :P, :], xp * cos + rot(xp) * sin], dim=-2)
+    return ap(q), ap(k)
+
+
+@pytest.mark.parametrize("side,heads,frames", [(224, 12, 3), (256, 6, 2), (64, 12, 5), (32, 16, 4)])
+def test_attention_with_rope(side, heads, frames):
+    n = side // 16
+    T, P, D = n * n + 5, 5, heads * 64
+    cos, sin = rope_tables(n, n)
+    cos, sin = cos.cuda(), sin.cuda()
+    qkv = (torch.randn(frames * T, 3 * D, device="cuda") * 1.5).to(torch.bfloat16)
+    out = attention(qkv, cos, sin, frames, T, P, heads).float()
+    x = qkv.float().view(frames, T, 3, heads, 64).permute(2, 0, 3, 1, 4)  # [3,B,H,T,64]
+    q, k = _rope_ref(x[0], x[1], cos, sin)
+    want = F.scaled_dot_product_attention(q, k, x[2], scale=0.125).permute(0, 2, 1, 3).reshape(frames * T, D)
+    e = rel_err(out, want)
+    assert e < 1.5e-2, f"attention rel err {e}"
+
+
+def test_rope_tables_match_hf_module():
+    from transformers import DINOv3ViTConfig
+    from transformers.models.dinov3_vit.modeling_dinov3_vit import DINOv3ViTRopePositionEmbedding
+    rope = DINOv3ViTRopePositionEmbedding(DINOv3ViTConfig(hidden_size=768, num_attention_heads=12)).eval()
+    cos, sin = rope(torch.zeros(1, 3, 224, 224))
+    c, s = rope_tables(14, 14)
+    np.testing.assert_allclose(cos[:, :32].numpy(), c.numpy(), atol=1e-6)
+    np.testing.assert_allclose(cos[:, 32:].numpy(), c.numpy(), atol=1e-6)
+    np.testing.assert_allclose(sin[:, :32].numpy(), s.numpy(), atol=1e-6)
+
+
+def test_preprocess_green_exact():
+    frames = oenc.synthetic_frames(3, 64, 96, seed=1, structured=False)
+    f = torch.from_numpy(frames).cuda()
+    A = torch.empty(3 * 4 * 6, 256, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().cbas_b200_preprocess_green(f.data_ptr(), A.data_ptr(), 3, 64, 96, 64 * 96 * 3, 96 * 3,
+                                                     stream()), "green")
+    g = torch.from_numpy(frames[..., 1].astype(np.float32))  # [3,64,96]
+    want = g.view(3, 4, 16, 6, 16).permute(0, 1, 3, 2, 4).reshape(3 * 24, 256)
+    assert torch.equal(A.float().cpu(), want)  # bytes are exact in bf16
+
+
+@pytest.mark.parametrize("H,W,S", [(256, 256, 224), (96, 128, 64), (224, 224, 224), (48, 48, 64)])
+def test_preprocess_resize_matches_oracle(H, W, S):
+    frames = oenc.synthetic_frames(2, H, W, seed=2)
+    want = oenc.preprocess_processor(frames, S)  # [2,3,S,S]
+    ns = S // 16
+    want = want.view(2, 3, ns, 16, ns, 16).permute(0, 2, 4, 1, 3, 5).reshape(2 * ns * ns, 768)
+    ymin, wy = aa_bilinear_taps(H, S)
+    xmin, wx = aa_bilinear_taps(W, S)
+    t = lambda a, dt: torch.from_numpy(a).to("cuda", dt).contiguous()
+    ymin_d, wy_d, xmin_d, wx_d = t(ymin, torch.int32), t(wy, torch.float32), t(xmin, torch.int32), t(wx, torch.float32)
+    f = torch.from_numpy(frames).cuda()
+    A = torch.empty(2 * ns * ns, 768, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().cbas_b200_preprocess_resize(
+        f.data_ptr(), A.data_ptr(), 2, H, W, H * W * 3, W * 3, S, ymin_d.data_ptr(), wy_d.data_ptr(), wy.shape[1],
+        xmin_d.data_ptr(), wx_d.data_ptr(), wx.shape[1], stream()), "resize")
+    got = A.float().cpu()
+    # <= 1 bf16 ulp: |x| <= 2.7 -> ulp 2^-7 at most
+    err = (got - want).abs()
+    assert float(err.max()) <= 2.0 ** -7 + 1e-6, float(err.max())
+    assert float((err / want.abs().clamp_min(0.25)).max()) < 2.0 ** -7
