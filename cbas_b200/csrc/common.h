@@ -34,6 +34,8 @@ struct GemmParams;
 int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, const GemmParams& p, int epi,
                 cudaStream_t stream, int prof_tag = PROF_OTHER);
 
+void set_gemm_cta_group(int cg);  // 0 auto, 1 single-CTA tiles, 2 CTA-pair tiles
+
 #define CBAS_CHECK(expr)                                   \
     do {                                                   \
         if (int _rc = ::cbas::check_cuda((expr), #expr)) return _rc; \

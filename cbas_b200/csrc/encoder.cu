@@ -271,6 +271,12 @@ int cbas_b200_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_
     return launch_gemm((const __nv_bfloat16*)a_dev, K, (const __nv_bfloat16*)w_dev, K, p, epi, (cudaStream_t)stream);
 }
 
+int cbas_b200_debug_gemm_cta_group(int32_t cg) {
+    if (cg < 0 || cg > 2) return fail("cta group must be 0 (auto), 1 or 2");
+    set_gemm_cta_group(cg);
+    return 0;
+}
+
 int cbas_b200_layernorm(const float* in_dev, const float* gamma_dev, const float* beta_dev, void* out_bf16_dev,
                         int32_t rows, int32_t D, float eps, void* stream) {
     return launch_layernorm<__nv_bfloat16>(in_dev, 1, gamma_dev, beta_dev, (__nv_bfloat16*)out_bf16_dev, rows, D, eps,

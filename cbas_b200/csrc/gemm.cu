@@ -9,6 +9,8 @@ namespace cbas {
 
 namespace {
 
+int g_force_cg = 0;  // 0 = automatic; 1 / 2 force the CTA-group size (tests, A/B timing)
+
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -26,55 +28,79 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// K-major bf16 matrix [rows, K] with row pitch ld elements; box = 64 (K) x box_rows, 128-byte swizzle.
-int make_tmap(CUtensorMap* map, const __nv_bfloat16* base, int rows, int K, int ld, int box_rows) {
+// Row-major matrix [rows, cols] with row pitch ld elements; box = box_cols x box_rows whose inner extent is
+// 128 bytes (64 bf16 or 32 fp32), 128-byte swizzle.  Used for the K-major operands and for the output slabs.
+int make_tmap(CUtensorMap* map, const void* base, bool f32, int rows, int cols, int ld, int box_cols, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__nv_bfloat16)};
-    cuuint32_t box[2] = {(cuuint32_t)GEMM_BLOCK_K, (cuuint32_t)box_rows};
+    const size_t es = f32 ? 4 : 2;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box,
-                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     return 0;
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int CG>
 int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-    // exact-erf GELU is ALU-heavy: give that epilogue 8 warps (two column slices per TMEM lane quarter)
-    constexpr int EW = 8;
-    using Cfg = GemmCfg<BLOCK_N>;
-    auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI, EW>;
+    using Cfg = GemmCfg<BLOCK_N, CG>;
+    auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI, CG>;
     static bool configured = false;  // per instantiation
     if (!configured) {
         CBAS_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured = true;
     }
-    const int m_blocks = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+    CUtensorMap tout = ta;  // unused by the direct-store (patch) epilogue
+    if (gemm_epi_staged(EPI)) {
+        const bool f32 = !gemm_epi_out_bf16(EPI);
+        if ((reinterpret_cast<uintptr_t>(p.out) & 15) || (p.ldo % (f32 ? 4 : 8)))
+            return fail("GEMM output must be 16-byte aligned with a 16-byte multiple row pitch");
+        if (int rc = make_tmap(&tout, p.out, f32, p.M, p.N, p.ldo, gemm_slab_cols(EPI), GEMM_BLOCK_M)) return rc;
+    }
+    const int m_blocks = (p.M + GEMM_BLOCK_M * CG - 1) / (GEMM_BLOCK_M * CG);
     const int tiles = m_blocks * (p.N / BLOCK_N);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, 128 + 32 * EW, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+    const int max_clusters = sm_count() / CG;
+    const int grid = CG * (tiles < max_clusters ? tiles : max_clusters);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, p);
     count_launch();
+    if (err != cudaSuccess) return check_cuda(err, "gemm_tcgen05_kernel launch");
     return check_cuda(cudaGetLastError(), "gemm_tcgen05_kernel launch");
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CG>
 int launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, const GemmParams& p, int epi,
               cudaStream_t stream) {
     CUtensorMap ta, tb;
-    if (int rc = make_tmap(&ta, A, p.M, p.K, lda, GEMM_BLOCK_M)) return rc;
-    if (int rc = make_tmap(&tb, W, p.N, p.K, ldw, BLOCK_N)) return rc;
+    if (int rc = make_tmap(&ta, A, false, p.M, p.K, lda, GEMM_BLOCK_K, GEMM_BLOCK_M)) return rc;
+    if (int rc = make_tmap(&tb, W, false, p.N, p.K, ldw, GEMM_BLOCK_K, BLOCK_N / CG)) return rc;
     switch (epi) {
-        case EPI_BIAS_BF16: return launch_one<BLOCK_N, EPI_BIAS_BF16>(ta, tb, p, stream);
-        case EPI_BIAS_GELU_BF16: return launch_one<BLOCK_N, EPI_BIAS_GELU_BF16>(ta, tb, p, stream);
-        case EPI_RESID_F32: return launch_one<BLOCK_N, EPI_RESID_F32>(ta, tb, p, stream);
-        case EPI_PATCH_F32: return launch_one<BLOCK_N, EPI_PATCH_F32>(ta, tb, p, stream);
-        case EPI_BIAS_F32: return launch_one<BLOCK_N, EPI_BIAS_F32>(ta, tb, p, stream);
+        case EPI_BIAS_BF16: return launch_one<BLOCK_N, EPI_BIAS_BF16, CG>(ta, tb, p, stream);
+        case EPI_BIAS_GELU_BF16: return launch_one<BLOCK_N, EPI_BIAS_GELU_BF16, CG>(ta, tb, p, stream);
+        case EPI_RESID_F32: return launch_one<BLOCK_N, EPI_RESID_F32, CG>(ta, tb, p, stream);
+        case EPI_PATCH_F32: return launch_one<BLOCK_N, EPI_PATCH_F32, CG>(ta, tb, p, stream);
+        case EPI_BIAS_F32: return launch_one<BLOCK_N, EPI_BIAS_F32, CG>(ta, tb, p, stream);
+        case EPI_BIAS_GELU_F32: return launch_one<BLOCK_N, EPI_BIAS_GELU_F32, CG>(ta, tb, p, stream);
     }
     return fail("unknown GEMM epilogue " + std::to_string(epi));
 }
+
 
 }  // namespace
 
@@ -85,10 +111,20 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
     if (p.K % GEMM_BLOCK_K != 0 || p.K <= 0) return fail("GEMM K must be a positive multiple of 64");
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) || (lda % 8) || (ldw % 8))
         return fail("GEMM operands must be 16-byte aligned with row pitch a multiple of 8 elements");
-    if (p.N % 256 == 0) return launch_bn<256>(A, lda, W, ldw, p, epi, stream);
-    if (p.N % 192 == 0) return launch_bn<192>(A, lda, W, ldw, p, epi, stream);
-    if (p.N % 128 == 0) return launch_bn<128>(A, lda, W, ldw, p, epi, stream);
+    // CTA pairs (256-row tiles) whenever there is enough work to fill the chip with them
+    const bool pair = g_force_cg ? g_force_cg == 2 : p.M >= 4096;
+    if (pair) {
+        if (p.N % 256 == 0) return launch_bn<256, 2>(A, lda, W, ldw, p, epi, stream);
+        if (p.N % 192 == 0) return launch_bn<192, 2>(A, lda, W, ldw, p, epi, stream);
+        if (p.N % 128 == 0) return launch_bn<128, 2>(A, lda, W, ldw, p, epi, stream);
+    } else {
+        if (p.N % 256 == 0) return launch_bn<256, 1>(A, lda, W, ldw, p, epi, stream);
+        if (p.N % 192 == 0) return launch_bn<192, 1>(A, lda, W, ldw, p, epi, stream);
+        if (p.N % 128 == 0) return launch_bn<128, 1>(A, lda, W, ldw, p, epi, stream);
+    }
     return fail("GEMM N must be a multiple of 128 (got " + std::to_string(p.N) + ")");
 }
+
+void set_gemm_cta_group(int cg) { g_force_cg = cg; }
 
 }  // namespace cbas

@@ -93,9 +93,12 @@ int cbas_b200_encoder_debug_hidden(cbas_encoder* enc, const uint8_t* frames_dev,
 
 /* ------------------------------------------------------------------------------------- kernel-level entry points
  * (used by the parity tests and by bench.py's roofline leg; same kernels the encoder launches) */
-/* out = epilogue(A[M,K] * W[N,K]^T + bias); epi: 0 bias->bf16, 1 bias+GELU(erf)->bf16, 2 f32 out += , 4 bias->f32 */
+/* out = epilogue(A[M,K] * W[N,K]^T + bias); epi: 0 bias->bf16, 1 bias+GELU(erf)->bf16, 2 f32 out += , 4 bias->f32,
+ * 5 bias+GELU->f32 */
 int cbas_b200_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_dev, void* out_dev, int32_t M,
                         int32_t N, int32_t K, int32_t epi, void* stream);
+/* Test knob: 0 = choose automatically (CTA pairs / tcgen05 cta_group::2 when M >= 4096), 1 or 2 = force. */
+int cbas_b200_debug_gemm_cta_group(int32_t cg);
 int cbas_b200_layernorm(const float* in_dev, const float* gamma_dev, const float* beta_dev, void* out_bf16_dev,
                         int32_t rows, int32_t D, float eps, void* stream);
 int cbas_b200_attention(const void* qkv_bf16_dev, void* out_bf16_dev, const float* rope_cos_dev,

@@ -10,7 +10,7 @@ def stream():
 
 
 def gemm(a_bf16, w_bf16, bias=None, epi=0, out=None):
-    """out = epilogue(a @ w.T + bias); epi 0 bf16, 1 gelu bf16, 2 f32 += , 4 f32."""
+    """out = epilogue(a @ w.T + bias); epi 0 bf16, 1 gelu bf16, 2 f32 += , 4 f32, 5 gelu f32."""
     M, K = a_bf16.shape
     N = w_bf16.shape[0]
     if out is None:

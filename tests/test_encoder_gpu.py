@@ -73,6 +73,15 @@ def test_against_reference_encode_file_fixture(golden_dir):
     assert cos >= 0.999 and rel <= 2e-2 and nn_ok
 
 
+def test_large_batch_uses_cta_pair_gemms():
+    # n*T >= 4096 rows switches the GEMMs to CTA-pair tiles; the small-batch result is the single-CTA path
+    enc = DinoEncoder("synthetic:vits16@5", "cuda", max_frames=24)
+    frames = torch.from_numpy(oenc.synthetic_frames(24, 224, 224, seed=9)).cuda()
+    big = enc.encode_u8(frames)            # 24*201 = 4824 rows -> pairs
+    small = torch.cat([enc.encode_u8(frames[i:i + 8]) for i in range(0, 24, 8)])  # 1608 rows -> single CTA
+    assert rel_err(big, small) < 1e-5
+
+
 def test_batch_independence_and_chunking():
     enc = DinoEncoder("synthetic:vits16@3", "cuda", max_frames=4)
     frames = torch.from_numpy(oenc.synthetic_frames(10, 64, 64, seed=8)).cuda()

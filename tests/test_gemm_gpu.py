@@ -4,7 +4,16 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+from cbas_b200 import _lib  # noqa: E402
 from tests.gpu_util import gemm, rel_err  # noqa: E402
+
+
+@pytest.fixture(params=[1, 2], ids=["cta1", "cta_pair"], autouse=True)
+def cta_group(request):
+    """Every case runs on single-CTA tiles (128 x N) and on CTA-pair tiles (tcgen05 cta_group::2, 256 x N)."""
+    _lib.check(_lib.lib().cbas_b200_debug_gemm_cta_group(request.param), "cta_group")
+    yield request.param
+    _lib.lib().cbas_b200_debug_gemm_cta_group(0)
 
 
 def _mk(M, N, K, seed=0):
@@ -36,6 +45,13 @@ def test_gemm_bf16_epilogues(epi):
     if epi == 1:
         want = torch.nn.functional.gelu(want)
     assert rel_err(out, want) < 6e-3  # bf16 output rounding (2^-9)
+
+
+def test_gemm_gelu_f32():
+    a, w, b = _mk(1029, 256, 1152, seed=4)
+    out = gemm(a, w, b, epi=5)
+    want = torch.nn.functional.gelu(a.float() @ w.float().T + b)
+    assert rel_err(out, want) < 2e-5  # fast erf: |erf error| <= 1.5e-7
 
 
 def test_gemm_residual_inplace():
