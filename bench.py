@@ -175,7 +175,9 @@ def main():
 
     side = SIDE
     src_hw = SRC_HW if args.preprocess == "processor" else (SIDE, SIDE)
-    enc = DinoEncoder(f"synthetic:{args.arch}", dev, preprocess=args.preprocess, image_size=side, max_frames=CHUNK)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):  # stdout carries exactly one JSON line
+        enc = DinoEncoder(f"synthetic:{args.arch}", dev, preprocess=args.preprocess, image_size=side, max_frames=CHUNK)
     a = ARCHITECTURES[args.arch]
     F = flops_per_frame(a["hidden_size"], a["num_hidden_layers"], a["intermediate_size"], side)
     peaks = load_peaks()

@@ -1,0 +1,252 @@
+// Fused ViT self-attention on tcgen05 for frames whose padded token count fits one MMA tile (T <= 256):
+// one persistent CTA per SM walks (frame, head) work items; per item
+//
+//   TMA      : Q (two 128-row tiles), K and V ([TK,64] each) of the head straight out of the fused QKV
+//              activation into a double-buffered shared-memory set (SWIZZLE_128B), one item ahead.
+//   tcgen05  : S_mt = Q_mt K^T  (128 x TK x 64, fp32 in TMEM) for both query tiles;
+//              O_mt = P_mt V    (128 x 64 x TK) with P read FROM TMEM (bf16 written over S by the softmax
+//              warps) and V consumed MN-major exactly as TMA laid it down - no transposes, no P in smem.
+//   softmax  : two warpgroups, one per query tile; a thread owns one query row, so the row max / sum need no
+//              shuffles: pass 1 reads S for the max, pass 2 re-reads S, exponentiates (exp2, scale folded),
+//              packs bf16 pairs and stores them over the columns of S already consumed.
+//   epilogue : O / rowsum -> bf16 -> [M, D] at column head*64, a full 128-byte line per thread.
+//
+// RoPE is NOT applied here: on this path the QKV GEMM epilogue rotates q and k on the fp32 accumulators
+// (EPI_QKV_ROPE_BF16), so each is rounded to bf16 once.  (The mma.sync kernel in attention.cuh keeps the
+// RoPE-in-prologue form and serves frames with more than 256 tokens.)
+//
+// TMEM map (512 columns): query tile mt owns columns [256*mt, 256*mt+256): S at +0..TK, P (bf16 pairs) at
+// +0..TK/2, O at +192..+256 (written only after the softmax has consumed S, read back by the same warps).
+// Reference semantics: HF modeling_dinov3_vit.py:316-329 (SDPA, scale 1/8, no mask, non-causal).
+#pragma once
+#include "ptx.cuh"
+
+namespace cbas {
+
+constexpr int ATC_THREADS = 384;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 softmax tile 0, 8-11 softmax tile 1
+constexpr int ATC_O_COL = 192;
+
+struct AttnTcParams {
+    const __nv_bfloat16* qkv;  // only for documentation; loads go through the tensor maps
+    __nv_bfloat16* out;        // [frames*T, D]
+    int frames, heads, T, TK, D;
+    float scale_log2;          // head_dim^-0.5 * log2(e)
+};
+
+__host__ __device__ inline int atc_set_bytes(int TK) { return 2 * 128 * 128 + 2 * TK * 128; }
+__host__ __device__ inline int atc_smem_bytes(int TK) { return 2 * atc_set_bytes(TK) + 1024 + 256; }
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 128} over qkv [M, 3D]
+                    const __grid_constant__ CUtensorMap tmap_kv,  // box {64, TK}
+                    const AttnTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int TK = p.TK, T = p.T;
+    const int set_bytes = atc_set_bytes(TK);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * set_bytes);
+    uint64_t* kv_full = bars;        // [2] TMA -> MMA
+    uint64_t* kv_empty = bars + 2;   // [2] MMA -> TMA
+    uint64_t* s_full = bars + 4;     // [2] per query tile: MMA -> softmax
+    uint64_t* p_full = bars + 6;     // [2] softmax -> MMA
+    uint64_t* o_full = bars + 8;     // [2] MMA -> epilogue
+    uint64_t* o_empty = bars + 10;   // [2] epilogue -> MMA (TMEM half free again)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_items = p.frames * p.heads;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_kv);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 4);
+            mbar_init(&o_full[i], 1);
+            mbar_init(&o_empty[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- TMA producer
+            int it = 0;
+            for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
+                const int b = it & 1;
+                const int f = w / p.heads, h = w % p.heads;
+                uint8_t* set = smem + b * set_bytes;
+                mbar_wait(&kv_empty[b], ((it >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[b], set_bytes);
+                const int row0 = f * T;
+                tma_load_2d(set, &tmap_q, &kv_full[b], h * 64, row0);
+                tma_load_2d(set + 16384, &tmap_q, &kv_full[b], h * 64, row0 + 128);
+                tma_load_2d(set + 32768, &tmap_kv, &kv_full[b], p.D + h * 64, row0);
+                tma_load_2d(set + 32768 + TK * 128, &tmap_kv, &kv_full[b], 2 * p.D + h * 64, row0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- MMA issuer
+            const uint32_t idesc_s = umma_idesc_bf16(128, TK);
+            const uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);
+            int it = 0;
+            for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
+                const int b = it & 1;
+                uint8_t* set = smem + b * set_bytes;
+                mbar_wait(&kv_full[b], (it >> 1) & 1);
+                tc_fence_after();
+                const uint64_t dk = umma_desc_sw128(smem_u32(set + 32768));
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    mbar_wait(&o_empty[mt], (it & 1) ^ 1);  // previous item's O (inside this S region) was drained
+                    tc_fence_after();
+                    const uint64_t dq = umma_desc_sw128(smem_u32(set + mt * 16384));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ss(tmem_base + 256 * mt, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                    umma_commit(&s_full[mt]);
+                }
+                const uint64_t dv = umma_desc_sw128_mn(smem_u32(set + 32768 + TK * 128));
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    mbar_wait(&p_full[mt], it & 1);
+                    tc_fence_after();
+                    for (int k = 0; k < TK / 16; ++k)  // 16 keys per MMA: 8 TMEM columns of P, 2048 B of V
+                        umma_bf16_ts(tmem_base + 256 * mt + ATC_O_COL, tmem_base + 256 * mt + 8 * k, dv + 128 * k,
+                                     idesc_o, k != 0);
+                    umma_commit(&o_full[mt]);
+                }
+                umma_commit(&kv_empty[b]);  // every MMA that reads this shared-memory set has retired
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------- softmax + epilogue warpgroups
+        const int mt = (warp - 4) >> 2;
+        const int quarter = warp & 3;
+        const int row = mt * 128 + quarter * 32 + lane;  // query token inside the frame
+        const bool warp_has_rows = (mt * 128 + quarter * 32) < T;
+        const uint32_t t_row = tmem_base + 256 * mt + (uint32_t(quarter * 32) << 16);
+        const float c = p.scale_log2;
+        int it = 0;
+        for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
+            const int f = w / p.heads, h = w % p.heads;
+            mbar_wait(&s_full[mt], it & 1);
+            tc_fence_after();
+            float inv_sum = 0.f;
+            if (warp_has_rows) {
+                // pass 1: row max over the T valid keys
+                float mx = -INFINITY;
+                for (int c0 = 0; c0 < TK; c0 += 32) {
+                    if (c0 + 32 <= TK) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_row + c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    } else {
+                        uint32_t v[16];
+                        tmem_ld_32x16(t_row + c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    }
+                }
+                const float mc = mx * c;
+                // pass 2: p = exp2(s*c - max*c), row sum, bf16 pairs written over the consumed part of S
+                float sum = 0.f;
+                for (int c0 = 0; c0 < TK; c0 += 32) {
+                    if (c0 + 32 <= TK) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_row + c0, v);
+                        tmem_ld_wait();
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float e0 = (c0 + j < T) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -mc)) : 0.f;
+                            const float e1 = (c0 + j + 1 < T) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), c, -mc)) : 0.f;
+                            sum += e0 + e1;
+                            pk[j >> 1] = pack_bf16(e0, e1);
+                        }
+                        tmem_st_32x16(t_row + (c0 >> 1), pk);
+                    } else {
+                        uint32_t v[16];
+                        tmem_ld_32x16(t_row + c0, v);
+                        tmem_ld_wait();
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            const float e0 = (c0 + j < T) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -mc)) : 0.f;
+                            const float e1 = (c0 + j + 1 < T) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), c, -mc)) : 0.f;
+                            sum += e0 + e1;
+                            pk[j >> 1] = pack_bf16(e0, e1);
+                        }
+                        tmem_st_32x8(t_row + (c0 >> 1), pk);
+                    }
+                }
+                tmem_st_wait();
+                inv_sum = 1.0f / sum;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[mt]);
+
+            mbar_wait(&o_full[mt], it & 1);
+            tc_fence_after();
+            if (warp_has_rows) {
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32(t_row + ATC_O_COL, v0);
+                tmem_ld_32x32(t_row + ATC_O_COL + 32, v1);
+                tmem_ld_wait();
+                if (row < T) {
+                    __nv_bfloat16* o = p.out + ((long long)f * T + row) * p.D + h * 64;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 q;
+                        q.x = pack_bf16(__uint_as_float(v0[j]) * inv_sum, __uint_as_float(v0[j + 1]) * inv_sum);
+                        q.y = pack_bf16(__uint_as_float(v0[j + 2]) * inv_sum, __uint_as_float(v0[j + 3]) * inv_sum);
+                        q.z = pack_bf16(__uint_as_float(v0[j + 4]) * inv_sum, __uint_as_float(v0[j + 5]) * inv_sum);
+                        q.w = pack_bf16(__uint_as_float(v0[j + 6]) * inv_sum, __uint_as_float(v0[j + 7]) * inv_sum);
+                        *reinterpret_cast<uint4*>(o + j) = q;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 q;
+                        q.x = pack_bf16(__uint_as_float(v1[j]) * inv_sum, __uint_as_float(v1[j + 1]) * inv_sum);
+                        q.y = pack_bf16(__uint_as_float(v1[j + 2]) * inv_sum, __uint_as_float(v1[j + 3]) * inv_sum);
+                        q.z = pack_bf16(__uint_as_float(v1[j + 4]) * inv_sum, __uint_as_float(v1[j + 5]) * inv_sum);
+                        q.w = pack_bf16(__uint_as_float(v1[j + 6]) * inv_sum, __uint_as_float(v1[j + 7]) * inv_sum);
+                        *reinterpret_cast<uint4*>(o + 32 + j) = q;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_empty[mt]);
+        }
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace cbas

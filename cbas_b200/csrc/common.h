@@ -34,6 +34,8 @@ struct GemmParams;
 int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, const GemmParams& p, int epi,
                 cudaStream_t stream, int prof_tag = PROF_OTHER);
 
+// Row-major [rows, cols] tensor map, box box_cols x box_rows with a 128-byte inner extent, SWIZZLE_128B.
+int make_tmap_2d(CUtensorMap* map, const void* base, bool f32, int rows, int cols, int ld, int box_cols, int box_rows);
 void set_gemm_cta_group(int cg);  // 0 auto, 1 single-CTA tiles, 2 CTA-pair tiles
 
 #define CBAS_CHECK(expr)                                   \

@@ -4,6 +4,7 @@
 // (modeling_dinov3_vit.py:530-555).  Residual stream is fp32; GEMM operands are bf16 with fp32 accumulation.
 #include "../../include/cbas_b200.h"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "common.h"
 #include "gemm_tcgen05.cuh"
 #include "layernorm.cuh"
@@ -74,6 +75,35 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* 
                                                                scale_log2);
     count_launch();
     return check_cuda(cudaGetLastError(), "attention_kernel launch");
+}
+
+int g_attention_impl = 0;  // 0 auto (tcgen05 when T <= 256), 1 mma.sync + RoPE prologue, 2 tcgen05
+
+bool use_attention_tc(int T) { return g_attention_impl == 2 || (g_attention_impl == 0 && T <= 256); }
+
+// qkv must already carry RoPE on q and k (EPI_QKV_ROPE_BF16)
+int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int T, int heads, cudaStream_t s) {
+    if (frames <= 0) return 0;
+    const int TK = (T + 15) & ~15;
+    if (TK > 256) return fail("tcgen05 attention handles at most 256 tokens per frame");
+    ProfScope prof(PROF_ATTENTION, s);
+    const int D = heads * 64;
+    const long long M = (long long)frames * T;
+    CUtensorMap tq, tkv;
+    if (int rc = make_tmap_2d(&tq, qkv, false, (int)M, 3 * D, 3 * D, 64, 128)) return rc;
+    if (int rc = make_tmap_2d(&tkv, qkv, false, (int)M, 3 * D, 3 * D, 64, TK)) return rc;
+    const int smem = atc_smem_bytes(TK);
+    static int configured_smem = 0;
+    if (smem > configured_smem) {
+        CBAS_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured_smem = smem;
+    }
+    AttnTcParams p{qkv, out, frames, heads, T, TK, D, 0.125f * 1.4426950408889634f};
+    const int items = frames * heads;
+    const int grid = items < sm_count() ? items : sm_count();
+    attention_tc_kernel<<<grid, ATC_THREADS, smem, s>>>(tq, tkv, p);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "attention_tc_kernel launch");
 }
 
 int launch_preprocess_green(const uint8_t* frames, __nv_bfloat16* A, int n, int H, int W, long long fs, int rs,
@@ -161,9 +191,19 @@ int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
                                                  c.ln_eps, s)) return rc;
     GemmParams p{};
     p.M = M; p.N = 3 * D; p.K = D; p.bias = (const float*)L.b_qkv; p.out = e->qkv; p.ldo = 3 * D;
-    if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16, s, PROF_QKV_GEMM)) return rc;
-    if (int rc = launch_attention(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n, e->T,
-                                  c.prefix_tokens, c.heads, s)) return rc;
+    if (use_attention_tc(e->T)) {
+        // RoPE on the fp32 accumulators in the QKV epilogue, then the tcgen05 attention kernel
+        p.rows_out = e->T; p.prefix = c.prefix_tokens; p.rope_cols = 2 * D;
+        p.rope_cos = (const float*)e->w.rope_cos; p.rope_sin = (const float*)e->w.rope_sin;
+        if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_QKV_ROPE_BF16, s, PROF_QKV_GEMM))
+            return rc;
+        if (int rc = launch_attention_tc(e->qkv, e->xn, n, e->T, c.heads, s)) return rc;
+    } else {
+        if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16, s, PROF_QKV_GEMM))
+            return rc;
+        if (int rc = launch_attention(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n,
+                                      e->T, c.prefix_tokens, c.heads, s)) return rc;
+    }
     p = GemmParams{};
     p.M = M; p.N = D; p.K = D; p.bias = (const float*)L.b_o; p.out = e->h; p.ldo = D;
     if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_o, D, p, EPI_RESID_F32, s, PROF_PROJ_GEMM)) return rc;
@@ -269,6 +309,29 @@ int cbas_b200_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_
     GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.bias = bias_dev; p.out = out_dev; p.ldo = N;
     return launch_gemm((const __nv_bfloat16*)a_dev, K, (const __nv_bfloat16*)w_dev, K, p, epi, (cudaStream_t)stream);
+}
+
+int cbas_b200_debug_attention_impl(int32_t impl) {
+    if (impl < 0 || impl > 2) return fail("attention impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
+    g_attention_impl = impl;
+    return 0;
+}
+
+int cbas_b200_attention_tc(const void* qkv_bf16_dev, void* out_bf16_dev, int32_t frames, int32_t T, int32_t heads,
+                           void* stream) {
+    return launch_attention_tc((const __nv_bfloat16*)qkv_bf16_dev, (__nv_bfloat16*)out_bf16_dev, frames, T, heads,
+                               (cudaStream_t)stream);
+}
+
+int cbas_b200_gemm_qkv_rope(const void* a_dev, const void* w_dev, const float* bias_dev, void* out_bf16_dev,
+                            int32_t M, int32_t N, int32_t K, const float* rope_cos_dev, const float* rope_sin_dev,
+                            int32_t T, int32_t prefix, int32_t rope_cols, void* stream) {
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.bias = bias_dev; p.out = out_bf16_dev; p.ldo = N;
+    p.rows_out = T; p.prefix = prefix; p.rope_cols = rope_cols; p.rope_cos = rope_cos_dev; p.rope_sin = rope_sin_dev;
+    if (N % 64 || rope_cols % 64) return fail("head slices are 64 columns wide");
+    return launch_gemm((const __nv_bfloat16*)a_dev, K, (const __nv_bfloat16*)w_dev, K, p, EPI_QKV_ROPE_BF16,
+                       (cudaStream_t)stream);
 }
 
 int cbas_b200_debug_gemm_cta_group(int32_t cg) {

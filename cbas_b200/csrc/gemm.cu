@@ -97,6 +97,7 @@ int launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
         case EPI_PATCH_F32: return launch_one<BLOCK_N, EPI_PATCH_F32, CG>(ta, tb, p, stream);
         case EPI_BIAS_F32: return launch_one<BLOCK_N, EPI_BIAS_F32, CG>(ta, tb, p, stream);
         case EPI_BIAS_GELU_F32: return launch_one<BLOCK_N, EPI_BIAS_GELU_F32, CG>(ta, tb, p, stream);
+        case EPI_QKV_ROPE_BF16: return launch_one<BLOCK_N, EPI_QKV_ROPE_BF16, CG>(ta, tb, p, stream);
     }
     return fail("unknown GEMM epilogue " + std::to_string(epi));
 }
@@ -126,5 +127,9 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
 }
 
 void set_gemm_cta_group(int cg) { g_force_cg = cg; }
+
+int make_tmap_2d(CUtensorMap* map, const void* base, bool f32, int rows, int cols, int ld, int box_cols, int box_rows) {
+    return make_tmap(map, base, f32, rows, cols, ld, box_cols, box_rows);
+}
 
 }  // namespace cbas

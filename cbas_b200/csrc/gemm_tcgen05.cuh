@@ -31,6 +31,7 @@ enum GemmEpilogue : int {
     EPI_PATCH_F32 = 3,       // resid_f32[row_map(m),n] = acc + bias[n]  (patch rows behind the prefix tokens)
     EPI_BIAS_F32 = 4,        // out_f32[m,n] = acc + bias[n]
     EPI_BIAS_GELU_F32 = 5,   // out_f32[m,n] = gelu_erf(acc + bias[n])
+    EPI_QKV_ROPE_BF16 = 6,   // EPI_BIAS_BF16 + DINOv3 RoPE on the q and k head slices of patch tokens
 };
 
 struct GemmParams {
@@ -40,6 +41,12 @@ struct GemmParams {
     int ldo;
     // EPI_PATCH_F32: A row m = frame*rows_in + p  ->  out row frame*rows_out + prefix + p
     int rows_in, rows_out, prefix;
+    // EPI_QKV_ROPE_BF16 (HF modeling_dinov3_vit.py:238-268): row m is token m % rows_out of its frame; tokens >=
+    // prefix are rotated in every 64-wide head slice of columns [0, rope_cols) (= the q and k thirds), on the
+    // fp32 accumulators:  x1' = x1 cos - x2 sin,  x2' = x2 cos + x1 sin,  tables [rows_out - prefix, 32] fp32.
+    const float* rope_cos;
+    const float* rope_sin;
+    int rope_cols;
 };
 
 constexpr int GEMM_BLOCK_M = 128;
@@ -49,7 +56,9 @@ constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_SLAB_BYTES = GEMM_BLOCK_M * 128;  // 128 rows x 128 B
 
-__host__ __device__ constexpr bool gemm_epi_out_bf16(int epi) { return epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16; }
+__host__ __device__ constexpr bool gemm_epi_out_bf16(int epi) {
+    return epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_QKV_ROPE_BF16;
+}
 __host__ __device__ constexpr bool gemm_epi_staged(int epi) { return epi != EPI_PATCH_F32; }
 __host__ __device__ constexpr int gemm_slab_cols(int epi) { return gemm_epi_out_bf16(epi) ? 64 : 32; }
 
@@ -237,6 +246,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         for (int j = 0; j < kSlabCols; j += 4) {
                             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
                             x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+                        }
+                    }
+                    if constexpr (EPI == EPI_QKV_ROPE_BF16) {
+                        // one slab = one head slice (64 columns): both rotation halves sit in this thread
+                        const int tok = (m_base + row_in_tile) % p.rows_out;
+                        if (n0 < p.rope_cols && tok >= p.prefix) {
+                            const float4* cs = reinterpret_cast<const float4*>(p.rope_cos + (tok - p.prefix) * 32);
+                            const float4* sn = reinterpret_cast<const float4*>(p.rope_sin + (tok - p.prefix) * 32);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 c4 = __ldg(cs + (j >> 2)), s4 = __ldg(sn + (j >> 2));
+                                const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float a = x[j + e], b = x[32 + j + e];
+                                    x[j + e] = a * cc[e] - b * ss[e];
+                                    x[32 + j + e] = b * cc[e] + a * ss[e];
+                                }
+                            }
                         }
                     }
                     if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_F32) {

@@ -46,3 +46,21 @@ def rel_err(got, want):
 def cosine_rows(a, b):
     a, b = a.double(), b.double()
     return (a * b).sum(-1) / (a.norm(dim=-1) * b.norm(dim=-1)).clamp_min(1e-30)
+
+
+def attention_tc(qkv_bf16, frames, T, heads):
+    D = heads * 64
+    out = torch.zeros(frames * T, D, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().cbas_b200_attention_tc(qkv_bf16.data_ptr(), out.data_ptr(), frames, T, heads, stream()),
+               "attention_tc")
+    return out
+
+
+def gemm_qkv_rope(a_bf16, w_bf16, bias, cos, sin, T, prefix, rope_cols):
+    M, K = a_bf16.shape
+    N = w_bf16.shape[0]
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().cbas_b200_gemm_qkv_rope(a_bf16.data_ptr(), w_bf16.data_ptr(), bias.data_ptr(),
+                                                  out.data_ptr(), M, N, K, cos.data_ptr(), sin.data_ptr(), T, prefix,
+                                                  rope_cols, stream()), "gemm_qkv_rope")
+    return out

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 from cbas_b200 import _lib  # noqa: E402
 from cbas_b200.encoder import aa_bilinear_taps, rope_tables  # noqa: E402
 from oracle import encoder as oenc  # noqa: E402
-from tests.gpu_util import attention, layernorm, rel_err, stream  # noqa: E402
+from tests.gpu_util import attention, attention_tc, gemm_qkv_rope, layernorm, rel_err, stream  # noqa: E402
 
 
 @pytest.mark.parametrize("D", [384, 768, 1024])
@@ -52,6 +52,34 @@ def test_attention_with_rope(side, heads, frames):
     want = F.scaled_dot_product_attention(q, k, x[2], scale=0.125).permute(0, 2, 1, 3).reshape(frames * T, D)
     e = rel_err(out, want)
     assert e < 1.5e-2, f"attention rel err {e}"
+
+
+@pytest.mark.parametrize("side,heads,frames", [(224, 12, 3), (224, 12, 40), (64, 6, 5), (160, 16, 7), (240, 12, 2)])
+def test_attention_tcgen05(side, heads, frames):
+    """tcgen05 kernel (S and PV on the 5th-gen tensor cores, P in TMEM) vs torch SDPA; no RoPE inside."""
+    n = side // 16
+    T, D = n * n + 5, heads * 64
+    qkv = (torch.randn(frames * T, 3 * D, device="cuda") * 1.5).to(torch.bfloat16)
+    out = attention_tc(qkv, frames, T, heads).float()
+    x = qkv.float().view(frames, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    want = F.scaled_dot_product_attention(x[0], x[1], x[2], scale=0.125).permute(0, 2, 1, 3).reshape(frames * T, D)
+    e = rel_err(out, want)
+    assert e < 1.5e-2, f"tcgen05 attention rel err {e}"
+
+
+def test_qkv_gemm_rope_epilogue():
+    n, heads, frames, P = 14, 6, 5, 5
+    T, D = n * n + P, heads * 64
+    cos, sin = rope_tables(n, n)
+    cos, sin = cos.cuda(), sin.cuda()
+    a = torch.randn(frames * T, D, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(3 * D, D, device="cuda") * 0.05).to(torch.bfloat16)
+    b = torch.randn(3 * D, device="cuda")
+    out = gemm_qkv_rope(a, w, b, cos, sin, T, P, 2 * D).float()
+    y = (a.float() @ w.float().T + b).view(frames, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    q, k = _rope_ref(y[0], y[1], cos, sin)
+    want = torch.stack([q, k, y[2]]).permute(1, 3, 0, 2, 4).reshape(frames * T, 3 * D)
+    assert rel_err(out, want) < 6e-3
 
 
 def test_rope_tables_match_hf_module():
