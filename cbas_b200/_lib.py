@@ -92,6 +92,7 @@ SIGNATURES = {
     "cbas_b200_head_create": (C.c_int, [C.POINTER(HeadCfg), C.POINTER(HeadWeights), C.POINTER(c_void_p)]),
     "cbas_b200_head_destroy": (None, [c_void_p]),
     "cbas_b200_head_infer": (C.c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
+    "cbas_b200_head_forward_windows": (C.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "cbas_b200_actogram_bins": (C.c_int, [c_void_p, c_int64, c_int32, c_int32, c_float, c_int64, c_void_p,
                                           c_void_p]),
 }

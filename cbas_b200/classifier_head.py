@@ -1,0 +1,184 @@
+"""ClassifierLSTMDeltas - host-side mirror of the reference head over the sm_100a C ABI.
+
+Mirrors `backend/classifier_head.py:57-172`: same constructor signature, same parameter names and shapes (a
+reference `model.pth` loads with `load_state_dict`, strict or not, exactly as `workthreads.py:441` does), same
+`forward(x[B,T,F]) -> (final_logits[B,C], rawm[B,2*Hs])` in eval mode.  The arithmetic runs in libcbas_b200.so
+(csrc/head.cu).  `infer_embeddings` is the fast path `infer_file` uses: the whole `cls` array in, one
+probability row per frame out, with infer_file's windowing, edge padding and temperature softmax on the GPU.
+
+Inference only: training mode (dropout, autograd) is the reference's job (head training is out of
+scope); calling forward() in train mode raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class ClassifierLSTMDeltas(nn.Module):
+    def __init__(self, in_features, out_features, seq_len=31, bottleneck_dim=128,
+                 dropout_p=0.15, use_acceleration=True, ema_alpha=0.3, center_window_size=5,
+                 lstm_hidden_size=64, lstm_layers=1):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.seq_len, self.sw = seq_len, center_window_size
+        self.hsl = seq_len // 2
+        self.use_acceleration = use_acceleration
+        self.ema_alpha = ema_alpha
+        self.bottleneck_dim = bottleneck_dim
+        self.lstm_hidden_size, self.lstm_layers = lstm_hidden_size, lstm_layers
+
+        # identical module tree to the reference so state_dict keys match (workthreads.py:856 model.pth)
+        self.cls_bottleneck = nn.Sequential(nn.Linear(in_features, bottleneck_dim), nn.GELU(), nn.Dropout(0.1))
+        self.delta_bottleneck = nn.Sequential(nn.Linear(in_features, bottleneck_dim), nn.GELU(), nn.Dropout(0.1))
+        if use_acceleration:
+            self.acc_bottleneck = nn.Sequential(nn.Linear(in_features, bottleneck_dim), nn.GELU(), nn.Dropout(0.1))
+        self.cls_ln = nn.LayerNorm(bottleneck_dim)
+        self.delta_ln = nn.LayerNorm(bottleneck_dim)
+        if use_acceleration:
+            self.acc_ln = nn.LayerNorm(bottleneck_dim)
+        augmented = bottleneck_dim * 3 if use_acceleration else bottleneck_dim * 2
+        self.lin0 = nn.Sequential(nn.Linear(augmented, 256), nn.GELU(), nn.Dropout(dropout_p))
+        self.gate = nn.Parameter(torch.tensor(0.2))
+        self.attention_head = nn.Linear(lstm_hidden_size * 2, 1)
+        self.attention_temp = nn.Parameter(torch.tensor(1.0))
+        self.lin1 = nn.Linear(in_features, out_features)
+        self.lin2 = nn.Linear(lstm_hidden_size * 2, out_features)
+        self.lstm = nn.LSTM(256, lstm_hidden_size, num_layers=lstm_layers, batch_first=True, bidirectional=True)
+        self._native = None
+        self._native_key = None
+        self.eval()
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    # ---- native handle management -----------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):  # .to() / .cuda() / .float() move the parameters: rebuild the handle lazily
+        self._drop_native()
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._drop_native()
+        return super().load_state_dict(*a, **k)
+
+    def _drop_native(self):
+        h = getattr(self, "_native", None)
+        if h:
+            try:
+                _lib.lib().cbas_b200_head_destroy(h)
+            except Exception:
+                pass
+        self._native = None
+        self._native_key = None
+
+    def __del__(self):
+        try:
+            self._drop_native()
+        except Exception:
+            pass
+
+    def _get_native(self) -> C.c_void_p:
+        dev = self.lin1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("cbas_b200.ClassifierLSTMDeltas runs on CUDA (sm_100a) only; move it with .to('cuda')")
+        key = (dev, tuple(int(p._version) for p in self.parameters()))
+        if self._native is not None and self._native_key == key:
+            return self._native
+        self._drop_native()
+        if not self.use_acceleration:
+            raise NotImplementedError("use_acceleration=False heads are not built yet")
+        lib = _lib.lib()
+        cfg = _lib.HeadCfg(self.in_features, self.out_features, self.seq_len, self.bottleneck_dim,
+                           self.lstm_hidden_size, self.sw, float(self.ema_alpha), 1, int(self.lstm_layers))
+        keep = []
+
+        def ptr(t: torch.Tensor) -> int:
+            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        w = _lib.HeadWeights()
+        w.cls_w, w.cls_b = ptr(self.cls_bottleneck[0].weight), ptr(self.cls_bottleneck[0].bias)
+        w.delta_w, w.delta_b = ptr(self.delta_bottleneck[0].weight), ptr(self.delta_bottleneck[0].bias)
+        w.acc_w, w.acc_b = ptr(self.acc_bottleneck[0].weight), ptr(self.acc_bottleneck[0].bias)
+        w.cls_ln_g, w.cls_ln_b = ptr(self.cls_ln.weight), ptr(self.cls_ln.bias)
+        w.delta_ln_g, w.delta_ln_b = ptr(self.delta_ln.weight), ptr(self.delta_ln.bias)
+        w.acc_ln_g, w.acc_ln_b = ptr(self.acc_ln.weight), ptr(self.acc_ln.bias)
+        w.lin0_w, w.lin0_b = ptr(self.lin0[0].weight), ptr(self.lin0[0].bias)
+        w.lin1_w, w.lin1_b = ptr(self.lin1.weight), ptr(self.lin1.bias)
+        w.lin2_w, w.lin2_b = ptr(self.lin2.weight), ptr(self.lin2.bias)
+        w.att_w, w.att_b = ptr(self.attention_head.weight), ptr(self.attention_head.bias)
+        w.w_ih_f, w.w_hh_f = ptr(self.lstm.weight_ih_l0), ptr(self.lstm.weight_hh_l0)
+        w.b_ih_f, w.b_hh_f = ptr(self.lstm.bias_ih_l0), ptr(self.lstm.bias_hh_l0)
+        w.w_ih_r, w.w_hh_r = ptr(self.lstm.weight_ih_l0_reverse), ptr(self.lstm.weight_hh_l0_reverse)
+        w.b_ih_r, w.b_hh_r = ptr(self.lstm.bias_ih_l0_reverse), ptr(self.lstm.bias_hh_l0_reverse)
+        w.gate = float(self.gate.detach().cpu())
+        w.attention_temp = float(self.attention_temp.detach().cpu())
+        handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            torch.cuda.synchronize(dev)  # the staged weight copies above must have landed before create() reads them
+            _lib.check(lib.cbas_b200_head_create(C.byref(cfg), C.byref(w), C.byref(handle)), "head_create")
+            torch.cuda.synchronize(dev)  # create() copies the weights; `keep` may go after this
+        self._native, self._native_key = handle, key
+        return handle
+
+    # ---- reference-compatible call ------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """x [B,T,F] -> (final_logits [B,C], rawm [B,2*Hs]); eval mode only."""
+        if self.training:
+            raise NotImplementedError("cbas_b200 head is inference-only; call .eval() (training stays in the reference)")
+        B, T, Fdim = x.shape
+        if T != self.seq_len or Fdim != self.in_features:
+            raise ValueError(f"expected windows of [{self.seq_len}, {self.in_features}], got [{T}, {Fdim}]")
+        h = self._get_native()
+        dev = self.lin1.weight.device
+        xd = x.to(device=dev, dtype=torch.float32).contiguous()
+        logits = torch.empty(B, self.out_features, device=dev, dtype=torch.float32)
+        rawm = torch.empty(B, 2 * self.lstm_hidden_size, device=dev, dtype=torch.float32)
+        _lib.check(_lib.lib().cbas_b200_head_forward_windows(
+            h, xd.data_ptr(), B, logits.data_ptr(), rawm.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+            "head_forward_windows")
+        return logits, rawm
+
+    # ---- fast path ----------------------------------------------------------------------------------------
+    def infer_embeddings(self, emb: torch.Tensor, temperature: float = 1.0,
+                         return_logits: bool = False):
+        """emb: float16 [N,F] on the head's device (the `cls` dataset as stored).  Returns probs float32 [N,C]
+        (and final logits when asked): for every frame the window [f-T/2, f+T/2] with replicate padding at both
+        ends, softmax(logits / max(1e-3, temperature)) - infer_file's numeric core (cbas.py:497-551)."""
+        dev = self.lin1.weight.device
+        if emb.dtype != torch.float16 or emb.dim() != 2 or emb.shape[1] != self.in_features:
+            raise ValueError(f"infer_embeddings expects float16 [N,{self.in_features}]")
+        emb = emb.to(dev).contiguous()
+        n = emb.shape[0]
+        probs = torch.empty(n, self.out_features, device=dev, dtype=torch.float32)
+        logits = torch.empty(n, self.out_features, device=dev, dtype=torch.float32) if return_logits else None
+        if n:
+            h = self._get_native()
+            _lib.check(_lib.lib().cbas_b200_head_infer(
+                h, emb.data_ptr(), n, float(temperature), probs.data_ptr(),
+                logits.data_ptr() if logits is not None else None, torch.cuda.current_stream(dev).cuda_stream),
+                "head_infer")
+        return (probs, logits) if return_logits else probs
+
+
+def actogram_bins(probs: torch.Tensor, behavior: int, threshold: float, bin_frames: int) -> torch.Tensor:
+    """Numeric core of Actogram.__init__ (cbas.py:969-999) on the GPU: probs float32 [N,C] (CUDA) -> int32 bin
+    counts [ceil(N / bin_frames)]."""
+    if probs.dtype != torch.float32 or probs.dim() != 2 or not probs.is_cuda:
+        raise ValueError("actogram_bins expects a float32 [N,C] CUDA tensor")
+    probs = probs.contiguous()
+    n, c = probs.shape
+    nb = (n + bin_frames - 1) // bin_frames if bin_frames > 0 else 0
+    bins = torch.zeros(nb, device=probs.device, dtype=torch.int32)
+    if n and nb:
+        _lib.check(_lib.lib().cbas_b200_actogram_bins(probs.data_ptr(), n, c, int(behavior), float(threshold),
+                                                      int(bin_frames), bins.data_ptr(),
+                                                      torch.cuda.current_stream(probs.device).cuda_stream),
+                   "actogram_bins")
+    return bins

@@ -163,6 +163,11 @@ void cbas_b200_head_destroy(cbas_head* head);
 int cbas_b200_head_infer(cbas_head* head, const void* emb_f16_dev, int64_t n_frames, float temperature,
                          float* probs_out_dev, float* logits_out_dev, void* stream);
 
+/* ClassifierLSTMDeltas.forward on arbitrary windows (classifier_head.py:150-172): x f32 [n_windows, seq_len, F]
+ * -> final_logits f32 [n_windows, C] and (optional) rawm f32 [n_windows, 2*lstm_hidden]. */
+int cbas_b200_head_forward_windows(cbas_head* head, const float* x_f32_dev, int64_t n_windows, float* logits_out_dev,
+                                   float* rawm_out_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ actogram
  * Replaces the numeric part of Actogram.__init__ (cbas.py:969-999): per frame
  * event = (p_b * [max_{b' != b} p_b' < p_b]) >= threshold ; bins[k] = sum of events over bin_frames frames
