@@ -1,0 +1,292 @@
+"""Host-side mirror of the hot-path entry points of `backend/cbas.py`:
+
+    encode_file(encoder, path, progress_callback=None) -> str | None        cbas.py:399-456
+    infer_file(file_path, model, dataset_name, behaviors, seq_len, device=None, temperature=1.0) -> str | None
+                                                                             cbas.py:458-572
+    Actogram(...).binned_activity                                            cbas.py:958-1007 (numeric part)
+
+Same signatures, file naming, return values and error behaviour as the reference, so `workthreads.EncodeThread`
+and `ClassificationThread` can call them unchanged; all GPU work goes through libcbas_b200.so.
+"""
+from __future__ import annotations
+
+import os
+import re
+import traceback
+from typing import Callable, Iterator, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import gui_state, store
+from .classifier_head import ClassifierLSTMDeltas, actogram_bins
+from .encoder import DinoEncoder
+
+CHUNK_SIZE = 512  # cbas.py:48
+
+
+# ----------------------------------------------------------------------------------------------- video decode
+class VideoReader:
+    """CPU video decode behind the two calls encode_file makes on decord.VideoReader (cbas.py:402,425):
+    len(reader) and reader.get_batch(indices) -> uint8 RGB [n,H,W,3].  Uses decord when it is installed (the
+    reference's decoder), OpenCV's FFmpeg backend otherwise; `.npy` files ([N,H,W,3] uint8) are read directly
+    (synthetic clips, tests).  Decode/IO errors propagate to the caller like the reference's."""
+
+    def __init__(self, path: str):
+        self.path = path
+        self._cap = None
+        self._arr = None
+        self._decord = None
+        self._pos = 0
+        if path.lower().endswith(".npy"):
+            self._arr = np.load(path, mmap_mode="r")
+            if self._arr.ndim != 4 or self._arr.shape[-1] != 3 or self._arr.dtype != np.uint8:
+                raise ValueError(f"{path}: expected a uint8 [N,H,W,3] array")
+            self._len = int(self._arr.shape[0])
+            return
+        try:
+            import decord  # type: ignore
+            self._decord = decord.VideoReader(path, ctx=decord.cpu(0))
+            self._len = len(self._decord)
+            return
+        except ImportError:
+            pass
+        import cv2
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        cap = cv2.VideoCapture(path)
+        if not cap.isOpened():
+            raise RuntimeError(f"could not open video '{path}'")
+        self._cap = cap
+        self._len = max(0, int(cap.get(cv2.CAP_PROP_FRAME_COUNT)))
+
+    def __len__(self) -> int:
+        return self._len
+
+    def get_batch(self, indices) -> np.ndarray:
+        idx = list(indices)
+        if self._arr is not None:
+            return np.ascontiguousarray(self._arr[idx[0]:idx[-1] + 1]) if idx else np.zeros((0,) + self._arr.shape[1:], np.uint8)
+        if self._decord is not None:
+            return self._decord.get_batch(idx).asnumpy()
+        import cv2
+        frames = []
+        for i in idx:
+            if i != self._pos:
+                self._cap.set(cv2.CAP_PROP_POS_FRAMES, i)
+                self._pos = i
+            ok, bgr = self._cap.read()
+            if not ok:
+                raise RuntimeError(f"decode failed at frame {i} of '{self.path}'")
+            self._pos += 1
+            frames.append(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB))
+        return np.stack(frames) if frames else np.zeros((0, 0, 0, 3), np.uint8)
+
+    def close(self):
+        if self._cap is not None:
+            self._cap.release()
+
+
+# ----------------------------------------------------------------------------------------------- encode
+def _make_pipeline(encoder, frame_hw: Tuple[int, int]):
+    """Streaming H2D -> ViT -> D2H pipeline for one encoder/geometry (cached on the encoder object)."""
+    from .pipeline import StreamedEncoder
+    cache = encoder.__dict__.setdefault("_pipelines", {})
+    pipe = cache.get(frame_hw)
+    if pipe is None:
+        pipe = StreamedEncoder(encoder, frame_hw, CHUNK_SIZE, depth=2)
+        cache[frame_hw] = pipe
+    return pipe
+
+
+def encode_file(encoder, path: str, progress_callback: Optional[Callable[[float], None]] = None) -> Optional[str]:
+    """Encode a video into `<video>_cls.h5` (cbas.py:399-456).
+
+    Returns the output path, or None for a video with no frames; decode, I/O and compute errors are raised after
+    the `.tmp` file has been removed.  The finished file appears atomically (os.replace).  `progress_callback`
+    receives the percentage after each 512-frame chunk has been decoded, from the calling thread."""
+    if not isinstance(encoder, DinoEncoder):
+        raise TypeError("cbas_b200.encode_file needs a cbas_b200.DinoEncoder (there is no PyTorch fallback path)")
+    reader = VideoReader(path)  # decoder errors propagate, as in the reference (cbas.py:400-402)
+    video_len = len(reader)
+    if video_len == 0:
+        print(f"Warning: Video {path} contains no frames. Skipping.")
+        return None
+
+    out_file_path = os.path.splitext(path)[0] + "_cls.h5"
+    tmp_file_path = out_file_path + ".tmp"
+    writer = None
+    try:
+        attrs = {}
+        if gui_state.proj:
+            attrs["encoder_model_identifier"] = gui_state.proj.encoder_model_identifier
+            attrs["schema_version"] = store.SCHEMA_VERSION
+        writer = store.EmbeddingWriter(tmp_file_path, encoder.hidden_size, attrs)
+
+        def chunks() -> Iterator[np.ndarray]:
+            for i in range(0, video_len, CHUNK_SIZE):
+                end_index = min(i + CHUNK_SIZE, video_len)
+                frames_np = reader.get_batch(range(i, end_index))
+                if progress_callback:
+                    progress_callback((end_index / video_len) * 100)
+                yield frames_np
+
+        def sink(emb: np.ndarray) -> None:
+            writer.append(emb)  # float32 -> float16 cast on store, like dset[-n:] = embeddings_out (cbas.py:438)
+            writer.flush()
+
+        it = chunks()
+        first = next(it)
+        pipe = _make_pipeline(encoder, tuple(first.shape[1:3]))
+
+        def all_chunks():
+            yield first
+            yield from it
+
+        with torch.no_grad():
+            pipe.run(all_chunks(), sink)
+        writer.close()
+        writer = None
+        os.replace(tmp_file_path, out_file_path)
+        print(f"Successfully encoded {os.path.basename(path)} to {os.path.basename(out_file_path)}")
+        return out_file_path
+    except Exception as e:
+        print(f"ERROR during encoding for {path}: {e}")
+        if writer is not None:
+            writer.abort()
+        if os.path.exists(tmp_file_path):
+            try:
+                os.remove(tmp_file_path)
+            except OSError:
+                pass
+        raise e
+    finally:
+        reader.close()
+
+
+# ----------------------------------------------------------------------------------------------- infer
+def _as_native_head(model, device: torch.device) -> ClassifierLSTMDeltas:
+    """Accept our head, or the reference's `classifier_head.ClassifierLSTMDeltas` instance (same state_dict)."""
+    if isinstance(model, ClassifierLSTMDeltas):
+        p = next(model.parameters())
+        return model if p.device == device else model.to(device)
+    if type(model).__name__.startswith("ClassifierLSTMDeltas"):
+        head = ClassifierLSTMDeltas(
+            in_features=model.in_features, out_features=model.out_features, seq_len=model.seq_len,
+            bottleneck_dim=model.cls_ln.normalized_shape[0], use_acceleration=model.use_acceleration,
+            ema_alpha=model.ema_alpha, center_window_size=model.sw,
+            lstm_hidden_size=model.lstm.hidden_size, lstm_layers=model.lstm.num_layers)
+        head.load_state_dict(model.state_dict(), strict=True)
+        return head.to(device)
+    raise TypeError(f"unsupported head architecture '{type(model).__name__}' (v3 inference needs ClassifierLSTMDeltas)")
+
+
+def infer_file(file_path: str, model, dataset_name: str, behaviors: List[str], seq_len: int, device=None,
+               temperature=1.0) -> Optional[str]:
+    """Run the head over one `_cls.h5` and write `<video>_<dataset_name>_outputs.csv` (cbas.py:458-572).
+
+    One probability row per frame (window centred on the frame, replicate padding at the ends of the video,
+    softmax(logits / max(1e-3, temperature))), columns = behaviors, no index.  Like the reference, any failure is
+    printed with its traceback and reported as None rather than raised."""
+    output_file = file_path.replace("_cls.h5", f"_{dataset_name}_outputs.csv")
+    if device is None:
+        device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    try:
+        import pandas as pd
+        if device.type != "cuda":
+            raise RuntimeError("cbas_b200.infer_file runs on CUDA only (no CPU fallback)")
+        head = _as_native_head(model, device)
+        if seq_len != head.seq_len:
+            raise ValueError(f"seq_len {seq_len} does not match the model's window ({head.seq_len})")
+        if len(behaviors) != head.out_features:
+            raise ValueError("behaviors does not match the model's output width")
+        with store.EmbeddingReader(file_path) as f:
+            total_frames = f.shape[0]
+            if total_frames == 0:
+                print(f"Warning: HDF5 file {file_path} is empty.")
+                return None
+            emb = np.ascontiguousarray(f.read(0, total_frames))
+        if emb.dtype != np.float16:
+            emb = emb.astype(np.float16)
+        emb_dev = torch.from_numpy(emb).to(device, non_blocking=False)
+        with torch.no_grad():
+            probs = head.infer_embeddings(emb_dev, temperature=float(temperature)).cpu().numpy()
+        if len(probs) != total_frames:
+            print(f"Warning: Prediction count ({len(probs)}) != Frame count ({total_frames}).")
+        pd.DataFrame(probs, columns=behaviors).to_csv(output_file, index=False)
+        return output_file
+    except Exception as e:
+        print(f"Error during buffered inference on {file_path}: {e}")
+        traceback.print_exc()
+        return None
+
+
+# ----------------------------------------------------------------------------------------------- actogram
+class Actogram:
+    """Numeric part of cbas.Actogram (cbas.py:958-1007): `binned_activity`, `binsize_frames`.  Same constructor
+    arguments; the PNG rendering (`blob`) is GUI work and stays None.  Events and bin sums are computed by the
+    CUDA kernel when a GPU is present."""
+
+    def __init__(self, behavior: str, framerate: float, start: float, binsize_minutes: int, threshold: float,
+                 lightcycle: str, plot_acrophase: bool = False, base_color: str = None, directory: str = None,
+                 model: str = None, preloaded_df=None):
+        self.behavior = behavior
+        self.framerate, self.start_hour_on_plot = float(framerate), float(start)
+        self.threshold, self.bin_size_minutes = float(threshold), int(binsize_minutes)
+        self.plot_acrophase = plot_acrophase
+        self.lightcycle_str = {"LL": "1" * 24, "DD": "0" * 24}.get(lightcycle, "1" * 12 + "0" * 12)
+        self.blob = None
+        self.binned_activity = []
+        if self.framerate <= 0 or self.bin_size_minutes <= 0:
+            return
+        self.binsize_frames = int(self.bin_size_minutes * self.framerate * 60)
+        if self.binsize_frames <= 0:
+            return
+        import pandas as pd
+        tables = []
+        if preloaded_df is not None:
+            if self.behavior in preloaded_df.columns:
+                tables.append(preloaded_df)
+        elif directory and model:
+            csvs = [os.path.join(directory, f) for f in os.listdir(directory) if f.endswith(f"_{model}_outputs.csv")]
+            if not csvs:
+                return
+            try:
+                csvs.sort(key=lambda p: int(re.search(r"_(\d+)_" + model, os.path.basename(p)).group(1)))
+            except (AttributeError, ValueError):
+                csvs.sort()
+            for p in csvs:
+                df = pd.read_csv(p)
+                if df.empty or self.behavior not in df.columns:
+                    continue
+                tables.append(df)
+        else:
+            return
+        if not tables:
+            return
+        # every table contributes its own frames; the other-behaviour maximum is taken inside each table's columns
+        events_parts = []
+        for df in tables:
+            cols = list(df.columns)
+            probs = np.ascontiguousarray(df.to_numpy(dtype=np.float32))
+            events_parts.append((probs, cols.index(self.behavior)))
+        self.binned_activity = [float(v) for v in _bin_tables(events_parts, self.threshold, self.binsize_frames)]
+
+
+def _bin_tables(parts, threshold: float, bin_frames: int) -> np.ndarray:
+    """Concatenate the per-file event streams and sum them in bins of bin_frames (last partial bin kept)."""
+    if len({(p.shape[1], b) for p, b in parts}) == 1 and torch.cuda.is_available():
+        probs = np.concatenate([p for p, _ in parts]) if len(parts) > 1 else parts[0][0]
+        return actogram_bins(torch.from_numpy(probs).cuda(), parts[0][1], threshold, bin_frames).cpu().numpy()
+    if not torch.cuda.is_available():
+        raise RuntimeError("cbas_b200.Actogram needs a CUDA device (no CPU fallback)")
+    # files with different column sets: per-file events on the GPU (bin size 1), then the bin sums
+    ev = [actogram_bins(torch.from_numpy(p).cuda(), b, threshold, 1) for p, b in parts]
+    ev = torch.cat(ev).to(torch.float32)
+    n = ev.numel()
+    nb = (n + bin_frames - 1) // bin_frames
+    pad = torch.zeros(nb * bin_frames - n, device=ev.device)
+    return torch.cat([ev, pad]).view(nb, bin_frames).sum(1).to(torch.int64).cpu().numpy()

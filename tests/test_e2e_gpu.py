@@ -1,0 +1,100 @@
+"""The whole drop-in path on the GPU through the public API: encode_file -> `_cls.h5` -> infer_file -> CSV ->
+Actogram, against the CPU oracle on the same synthetic clip, plus the worker-thread chain."""
+import os
+import time
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from cbas_b200 import bundle, cbas, gui_state, store, workthreads  # noqa: E402
+from cbas_b200.classifier_head import ClassifierLSTMDeltas  # noqa: E402
+from cbas_b200.encoder import DinoEncoder  # noqa: E402
+from oracle import actogram as oact  # noqa: E402
+from oracle import encoder as oenc  # noqa: E402
+from oracle import head as ohead  # noqa: E402
+
+BEHAVIORS = ["eating", "drinking", "rearing", "climbing", "digging", "nesting", "resting", "grooming", "background"]
+
+
+def test_encode_infer_actogram_chain(tmp_path, monkeypatch):
+    model = oenc.build_hf_model("vitb16", seed=0, init_scale=3.0)
+    frames = oenc.synthetic_frames(70, 64, 64, seed=11)
+    clip = str(tmp_path / "cam1_00001.npy")
+    np.save(clip, frames)
+    monkeypatch.setattr(gui_state, "proj", types.SimpleNamespace(encoder_model_identifier="synthetic:vitb16"))
+    enc = DinoEncoder.from_hf_model(model, "cuda", max_frames=32)
+    monkeypatch.setattr(cbas, "CHUNK_SIZE", 32)  # three chunks (32+32+6) through the double-buffered pipeline
+    progress = []
+    out = cbas.encode_file(enc, clip, progress.append)
+    assert out == str(tmp_path / "cam1_00001_cls.h5") and progress[-1] == 100.0 and len(progress) == 3
+    with store.EmbeddingReader(out) as r:
+        assert r.shape == (70, 768) and r.attrs["encoder_model_identifier"] == "synthetic:vitb16"
+        emb = r.read(0, 70)
+    want = oenc.encode(model, frames, mode="reference")
+    rel = np.abs(emb.astype(np.float32) - want).max() / np.abs(want).max()
+    cos = (emb.astype(np.float32) * want).sum(1) / (np.linalg.norm(emb.astype(np.float32), axis=1) * np.linalg.norm(want, axis=1))
+    print(f"[parity] encode_file -> h5: min cosine {cos.min():.6f} max|d|/max|ref| {rel:.3e}")
+    assert cos.min() >= 0.999 and rel <= 2e-2
+
+    sd = ohead.make_head_state(768, 9, 128, 64, seed=4, scale=2.0)
+    head = ClassifierLSTMDeltas(768, 9, seq_len=31)
+    head.load_state_dict(sd)
+    csv = cbas.infer_file(out, head, "JonesLabModel", BEHAVIORS, 31, device=torch.device("cuda"), temperature=1.4)
+    assert csv == str(tmp_path / "cam1_00001_JonesLabModel_outputs.csv")
+    import pandas as pd
+    df = pd.read_csv(csv)
+    assert list(df.columns) == BEHAVIORS and len(df) == 70
+    want_p = ohead.infer_windows(emb, sd, seq_len=31, temperature=1.4)  # the oracle head on the SAME stored f16 rows
+    assert np.abs(df.to_numpy() - want_p).max() <= 1e-3
+    assert (df.to_numpy().argmax(1) == want_p.argmax(1)).mean() >= 0.999
+
+    act = cbas.Actogram("resting", framerate=0.1, start=0.0, binsize_minutes=2, threshold=0.1, lightcycle="LD",
+                        preloaded_df=df, model="JonesLabModel")
+    bs = oact.binsize_frames(2, 0.1)
+    assert act.binsize_frames == bs == 12
+    np.testing.assert_array_equal(np.array(act.binned_activity, np.int64),
+                                  oact.actogram_bins(df.to_numpy(dtype=np.float32), BEHAVIORS.index("resting"), 0.1, bs))
+    act2 = cbas.Actogram("resting", 0.1, 0.0, 2, 0.1, "LD", directory=str(tmp_path), model="JonesLabModel")
+    assert act2.binned_activity == act.binned_activity
+
+
+def test_worker_threads_encode_then_classify(tmp_path, monkeypatch):
+    frames = oenc.synthetic_frames(40, 64, 64, seed=12)
+    clips = []
+    for i in range(2):
+        p = str(tmp_path / f"cam_{i:05d}.npy")
+        np.save(p, frames[i * 20:(i + 1) * 20])
+        clips.append(p)
+    sd = ohead.make_head_state(384, 4, 128, 64, seed=6)
+    head = ClassifierLSTMDeltas(384, 4, seq_len=31)
+    head.load_state_dict(sd)
+    mdir = str(tmp_path / "models" / "M")
+    bundle.save_model_bundle(mdir, head, "M", ["a", "b", "c", "d"], 31, "synthetic:vits16", 1.0)
+    monkeypatch.setattr(gui_state, "proj", types.SimpleNamespace(encoder_model_identifier="synthetic:vits16"))
+    monkeypatch.setattr(gui_state, "dino_encoder", DinoEncoder("synthetic:vits16", "cuda", max_frames=32))
+    monkeypatch.setattr(gui_state, "live_inference_model_name", "M")
+    gui_state.encode_tasks[:] = clips + [str(tmp_path / "missing.mp4")]
+    gui_state.classify_tasks[:] = []
+    enc_t = workthreads.EncodeThread("cuda", poll_seconds=0.01)
+    cls_t = workthreads.ClassificationThread("cuda", {"M": mdir}, poll_seconds=0.01)
+    enc_t.start()
+    cls_t.start()
+    want = [p.replace(".npy", "_M_outputs.csv") for p in clips]
+    for _ in range(3000):
+        if all(os.path.exists(w) for w in want):
+            break
+        time.sleep(0.01)
+    enc_t.stop()
+    cls_t.stop()
+    enc_t.join(5)
+    cls_t.join(5)
+    assert all(os.path.exists(w) for w in want)           # the bad path was logged and skipped
+    import pandas as pd
+    for w in want:
+        df = pd.read_csv(w)
+        assert list(df.columns) == ["a", "b", "c", "d"] and len(df) == 20
+        np.testing.assert_allclose(df.to_numpy().sum(1), 1.0, atol=1e-5)
