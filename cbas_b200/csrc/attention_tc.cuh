@@ -11,9 +11,11 @@
 //              packs bf16 pairs and stores them over the columns of S already consumed.
 //   epilogue : O / rowsum -> bf16 -> [M, D] at column head*64, a full 128-byte line per thread.
 //
-// RoPE is NOT applied here: on this path the QKV GEMM epilogue rotates q and k on the fp32 accumulators
-// (EPI_QKV_ROPE_BF16), so each is rounded to bf16 once.  (The mma.sync kernel in attention.cuh keeps the
-// RoPE-in-prologue form and serves frames with more than 256 tokens.)
+//   RoPE     : attention prologue, in shared memory.  While the tensor core runs PV of item i, the softmax warps
+//              rotate the Q and K rows of item i+1 in place (rotate-half form, fp32 math, cos/sin held as
+//              half2 pairs in shared memory, built once per CTA from the fp32 tables), fence them to the
+//              async proxy and release the MMA warp through an mbarrier.  Rows of prefix tokens and rows past
+//              the frame are left alone.  (Pass null tables to skip RoPE, e.g. when the QKV epilogue did it.)
 //
 // TMEM map (512 columns): query tile mt owns columns [256*mt, 256*mt+256): S at +0..TK, P (bf16 pairs) at
 // +0..TK/2, O at +192..+256 (written only after the softmax has consumed S, read back by the same warps).
@@ -31,10 +33,42 @@ struct AttnTcParams {
     __nv_bfloat16* out;        // [frames*T, D]
     int frames, heads, T, TK, D;
     float scale_log2;          // head_dim^-0.5 * log2(e)
+    const float* rope_cos;     // [T - prefix, 32] fp32 or null (no RoPE in this kernel)
+    const float* rope_sin;
+    int prefix;
 };
 
 __host__ __device__ inline int atc_set_bytes(int TK) { return 2 * 128 * 128 + 2 * TK * 128; }
-__host__ __device__ inline int atc_smem_bytes(int TK) { return 2 * atc_set_bytes(TK) + 1024 + 256; }
+__host__ __device__ inline int atc_rope_bytes(int T, int prefix) { return ((T - prefix) * 32 * 4 + 127) & ~127; }
+__host__ __device__ inline int atc_smem_bytes(int TK, int T, int prefix, bool rope) {
+    return 2 * atc_set_bytes(TK) + (rope ? atc_rope_bytes(T, prefix) : 0) + 1024 + 256;
+}
+
+// Rotate the patch-token rows of one [rows,64] bf16 tile in place.  `u` enumerates (row, chunk pair): a warp
+// covers 8 consecutive rows x 4 chunk pairs, so the 16-byte shared-memory accesses are conflict-free under
+// the 128-byte swizzle.  cs2 holds (cos, sin) half2 pairs, 32 per patch token.
+__device__ __forceinline__ void atc_rope_unit(uint8_t* tile, int row, int c, const __half2* cs2) {
+    uint8_t* r = tile + row * 128;
+    const int sw = row & 7;
+    uint4* plo = reinterpret_cast<uint4*>(r + ((c ^ sw) << 4));
+    uint4* phi = reinterpret_cast<uint4*>(r + (((c + 4) ^ sw) << 4));
+    uint4 lo = *plo, hi = *phi;
+    const uint4 t0 = *reinterpret_cast<const uint4*>(cs2 + 8 * c);      // 4 (cos,sin) pairs
+    const uint4 t1 = *reinterpret_cast<const uint4*>(cs2 + 8 * c + 4);  // 4 more
+    const uint32_t tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+    uint32_t* l = reinterpret_cast<uint32_t*>(&lo);
+    uint32_t* h = reinterpret_cast<uint32_t*>(&hi);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 a = unpack_bf16(l[i]), b = unpack_bf16(h[i]);
+        const float2 cs0 = __half22float2(*reinterpret_cast<const __half2*>(&tw[2 * i]));
+        const float2 cs1 = __half22float2(*reinterpret_cast<const __half2*>(&tw[2 * i + 1]));
+        l[i] = pack_bf16(a.x * cs0.x - b.x * cs0.y, a.y * cs1.x - b.y * cs1.y);
+        h[i] = pack_bf16(b.x * cs0.x + a.x * cs0.y, b.y * cs1.x + a.y * cs1.y);
+    }
+    *plo = lo;
+    *phi = hi;
+}
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 128} over qkv [M, 3D]
@@ -44,14 +78,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int TK = p.TK, T = p.T;
     const int set_bytes = atc_set_bytes(TK);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * set_bytes);
-    uint64_t* kv_full = bars;        // [2] TMA -> MMA
+    const bool rope = p.rope_cos != nullptr;
+    __half2* rope_tab = reinterpret_cast<__half2*>(smem + 2 * set_bytes);  // [T - prefix][32] (cos, sin)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * set_bytes + (rope ? atc_rope_bytes(T, p.prefix) : 0));
+    uint64_t* kv_full = bars;        // [2] TMA -> (softmax warps, then) MMA
     uint64_t* kv_empty = bars + 2;   // [2] MMA -> TMA
     uint64_t* s_full = bars + 4;     // [2] per query tile: MMA -> softmax
     uint64_t* p_full = bars + 6;     // [2] softmax -> MMA
     uint64_t* o_full = bars + 8;     // [2] MMA -> epilogue
     uint64_t* o_empty = bars + 10;   // [2] epilogue -> MMA (TMEM half free again)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* qk_ready = bars + 12;  // [2] softmax warps -> MMA: Q and K of this set are rotated
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_items = p.frames * p.heads;
@@ -68,8 +105,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             mbar_init(&p_full[i], 4);
             mbar_init(&o_full[i], 1);
             mbar_init(&o_empty[i], 4);
+            mbar_init(&qk_ready[i], 8);
         }
         fence_mbar_init();
+    }
+    if (rope) {
+        const int n = (T - p.prefix) * 32;
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            rope_tab[i] = __floats2half2_rn(__ldg(p.rope_cos + i), __ldg(p.rope_sin + i));
     }
     if (warp == 2) {
         tmem_alloc(tmem_ptr_smem, 512);
@@ -106,7 +149,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
                 const int b = it & 1;
                 uint8_t* set = smem + b * set_bytes;
-                mbar_wait(&kv_full[b], (it >> 1) & 1);
+                mbar_wait(rope ? &qk_ready[b] : &kv_full[b], (it >> 1) & 1);
                 tc_fence_after();
                 const uint64_t dk = umma_desc_sw128(smem_u32(set + 32768));
 #pragma unroll
@@ -140,6 +183,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
         const bool warp_has_rows = (mt * 128 + quarter * 32) < T;
         const uint32_t t_row = tmem_base + 256 * mt + (uint32_t(quarter * 32) << 16);
         const float c = p.scale_log2;
+        const int wtid = threadIdx.x - 128;  // 0..255 over both softmax warpgroups
+        // rotate Q (256 rows in two tiles) and K (TK rows) of the item that sits in buffer set `b`
+        auto rotate_set = [&](int b, int iter) {
+            mbar_wait(&kv_full[b], (iter >> 1) & 1);
+            uint8_t* set = smem + b * set_bytes;
+            const int units = (256 + TK) * 4;
+            for (int u = wtid; u < units; u += 256) {
+                const int row = u >> 2, cpair = u & 3;
+                const int tok = row < 256 ? row : row - 256;
+                if (tok >= p.prefix && tok < T)
+                    atc_rope_unit(row < 256 ? set : set + 32768 - 256 * 128, row, cpair, rope_tab + (tok - p.prefix) * 32);
+            }
+            fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qk_ready[b]);
+        };
+        if (rope && (int)blockIdx.x < num_items) rotate_set(0, 0);
         int it = 0;
         for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
             const int f = w / p.heads, h = w % p.heads;
@@ -150,7 +210,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                 // pass 1: row max over the T valid keys
                 float mx = -INFINITY;
                 for (int c0 = 0; c0 < TK; c0 += 32) {
-                    if (c0 + 32 <= TK) {
+                    if (c0 + 32 <= T) {  // chunk entirely inside the frame: no masking
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_row + c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2)
+                            mx = fmaxf(mx, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+                    } else if (c0 + 32 <= TK) {
                         uint32_t v[32];
                         tmem_ld_32x32(t_row + c0, v);
                         tmem_ld_wait();
@@ -170,7 +237,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                 // pass 2: p = exp2(s*c - max*c), row sum, bf16 pairs written over the consumed part of S
                 float sum = 0.f;
                 for (int c0 = 0; c0 < TK; c0 += 32) {
-                    if (c0 + 32 <= TK) {
+                    if (c0 + 32 <= T) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_row + c0, v);
+                        tmem_ld_wait();
+                        uint32_t pk[16];
+                        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), c, -mc));
+                            const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), c, -mc));
+                            s0 += e0;
+                            s1 += e1;
+                            pk[j >> 1] = pack_bf16(e0, e1);
+                        }
+                        sum += s0 + s1;
+                        tmem_st_32x16(t_row + (c0 >> 1), pk);
+                    } else if (c0 + 32 <= TK) {
                         uint32_t v[32];
                         tmem_ld_32x32(t_row + c0, v);
                         tmem_ld_wait();
@@ -204,6 +287,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[mt]);
+
+            // RoPE prologue of the NEXT item, hidden behind this item's PV MMAs
+            if (rope && w + (int)gridDim.x < num_items) rotate_set((it + 1) & 1, it + 1);
 
             mbar_wait(&o_full[mt], it & 1);
             tc_fence_after();

@@ -77,12 +77,14 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* 
     return check_cuda(cudaGetLastError(), "attention_kernel launch");
 }
 
-int g_attention_impl = 0;  // 0 auto (tcgen05 when T <= 256), 1 mma.sync + RoPE prologue, 2 tcgen05
+int g_attention_impl = 0;  // 0 auto (tcgen05 when T <= 256), 1 mma.sync + RoPE prologue, 2 tcgen05, 3 tcgen05 + epilogue RoPE
+bool g_rope_in_epilogue = false;
 
-bool use_attention_tc(int T) { return g_attention_impl == 2 || (g_attention_impl == 0 && T <= 256); }
+bool use_attention_tc(int T) { return g_attention_impl >= 2 || (g_attention_impl == 0 && T <= 256); }
 
-// qkv must already carry RoPE on q and k (EPI_QKV_ROPE_BF16)
-int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int T, int heads, cudaStream_t s) {
+// cs/sn: RoPE tables applied in the kernel's prologue, or null when q and k arrive rotated (EPI_QKV_ROPE_BF16)
+int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* cs, const float* sn, int frames,
+                        int T, int prefix, int heads, cudaStream_t s) {
     if (frames <= 0) return 0;
     const int TK = (T + 15) & ~15;
     if (TK > 256) return fail("tcgen05 attention handles at most 256 tokens per frame");
@@ -92,13 +94,17 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames
     CUtensorMap tq, tkv;
     if (int rc = make_tmap_2d(&tq, qkv, false, (int)M, 3 * D, 3 * D, 64, 128)) return rc;
     if (int rc = make_tmap_2d(&tkv, qkv, false, (int)M, 3 * D, 3 * D, 64, TK)) return rc;
-    const int smem = atc_smem_bytes(TK);
+    const bool rope = cs != nullptr && sn != nullptr;
+    if (rope && (prefix < 0 || prefix >= T)) return fail("attention: bad prefix token count");
+    const int smem = atc_smem_bytes(TK, T, prefix, rope);
+    if (smem > 232448) return fail("attention: frame does not fit in shared memory");
     static int configured_smem = 0;
     if (smem > configured_smem) {
         CBAS_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured_smem = smem;
     }
-    AttnTcParams p{qkv, out, frames, heads, T, TK, D, 0.125f * 1.4426950408889634f};
+    AttnTcParams p{qkv, out, frames, heads, T, TK, D, 0.125f * 1.4426950408889634f, rope ? cs : nullptr,
+                   rope ? sn : nullptr, prefix};
     const int items = frames * heads;
     const int grid = items < sm_count() ? items : sm_count();
     attention_tc_kernel<<<grid, ATC_THREADS, smem, s>>>(tq, tkv, p);
@@ -191,13 +197,19 @@ int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
                                                  c.ln_eps, s)) return rc;
     GemmParams p{};
     p.M = M; p.N = 3 * D; p.K = D; p.bias = (const float*)L.b_qkv; p.out = e->qkv; p.ldo = 3 * D;
-    if (use_attention_tc(e->T)) {
+    if (use_attention_tc(e->T) && g_rope_in_epilogue) {
         // RoPE on the fp32 accumulators in the QKV epilogue, then the tcgen05 attention kernel
         p.rows_out = e->T; p.prefix = c.prefix_tokens; p.rope_cols = 2 * D;
         p.rope_cos = (const float*)e->w.rope_cos; p.rope_sin = (const float*)e->w.rope_sin;
         if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_QKV_ROPE_BF16, s, PROF_QKV_GEMM))
             return rc;
-        if (int rc = launch_attention_tc(e->qkv, e->xn, n, e->T, c.heads, s)) return rc;
+        if (int rc = launch_attention_tc(e->qkv, e->xn, nullptr, nullptr, n, e->T, c.prefix_tokens, c.heads, s)) return rc;
+    } else if (use_attention_tc(e->T)) {
+        // plain QKV projection; the tcgen05 attention kernel rotates q and k in its prologue
+        if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16, s, PROF_QKV_GEMM))
+            return rc;
+        if (int rc = launch_attention_tc(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n,
+                                         e->T, c.prefix_tokens, c.heads, s)) return rc;
     } else {
         if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16, s, PROF_QKV_GEMM))
             return rc;
@@ -312,15 +324,18 @@ int cbas_b200_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_
 }
 
 int cbas_b200_debug_attention_impl(int32_t impl) {
-    if (impl < 0 || impl > 2) return fail("attention impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
+    if (impl < 0 || impl > 3)
+        return fail("attention impl must be 0 (auto), 1 (mma.sync), 2 (tcgen05) or 3 (tcgen05, RoPE in the QKV epilogue)");
     g_attention_impl = impl;
+    g_rope_in_epilogue = impl == 3;
     return 0;
 }
 
-int cbas_b200_attention_tc(const void* qkv_bf16_dev, void* out_bf16_dev, int32_t frames, int32_t T, int32_t heads,
+int cbas_b200_attention_tc(const void* qkv_bf16_dev, void* out_bf16_dev, const float* rope_cos_dev,
+                           const float* rope_sin_dev, int32_t frames, int32_t T, int32_t prefix, int32_t heads,
                            void* stream) {
-    return launch_attention_tc((const __nv_bfloat16*)qkv_bf16_dev, (__nv_bfloat16*)out_bf16_dev, frames, T, heads,
-                               (cudaStream_t)stream);
+    return launch_attention_tc((const __nv_bfloat16*)qkv_bf16_dev, (__nv_bfloat16*)out_bf16_dev, rope_cos_dev,
+                               rope_sin_dev, frames, T, prefix, heads, (cudaStream_t)stream);
 }
 
 int cbas_b200_gemm_qkv_rope(const void* a_dev, const void* w_dev, const float* bias_dev, void* out_bf16_dev,

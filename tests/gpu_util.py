@@ -48,11 +48,13 @@ def cosine_rows(a, b):
     return (a * b).sum(-1) / (a.norm(dim=-1) * b.norm(dim=-1)).clamp_min(1e-30)
 
 
-def attention_tc(qkv_bf16, frames, T, heads):
+def attention_tc(qkv_bf16, frames, T, heads, cos=None, sin=None, prefix=0):
     D = heads * 64
     out = torch.zeros(frames * T, D, device="cuda", dtype=torch.bfloat16)
-    _lib.check(_lib.lib().cbas_b200_attention_tc(qkv_bf16.data_ptr(), out.data_ptr(), frames, T, heads, stream()),
-               "attention_tc")
+    _lib.check(_lib.lib().cbas_b200_attention_tc(qkv_bf16.data_ptr(), out.data_ptr(),
+                                                 cos.data_ptr() if cos is not None else None,
+                                                 sin.data_ptr() if sin is not None else None, frames, T, prefix, heads,
+                                                 stream()), "attention_tc")
     return out
 
 

@@ -15,7 +15,7 @@ from oracle import encoder as oenc  # noqa: E402
 from tests.gpu_util import cosine_rows, rel_err  # noqa: E402
 
 
-@pytest.fixture(params=[2, 1], ids=["attn_tcgen05", "attn_mma_sync"])
+@pytest.fixture(params=[2, 1, 3], ids=["attn_tcgen05", "attn_mma_sync", "attn_tcgen05_epilogue_rope"])
 def attention_impl(request):
     """Both attention kernels: tcgen05 (RoPE in the QKV epilogue) and mma.sync (RoPE in its prologue)."""
     from cbas_b200 import _lib
@@ -39,7 +39,7 @@ def _report(tag, got, want):
 @pytest.mark.parametrize("arch,side,n,scale", [("vits16", 64, 5, 4.0), ("vitb16", 224, 4, 3.0), ("vitb16", 256, 3, 1.0),
                                               ("vitl16", 96, 3, 2.0)])
 def test_reference_mode_parity(arch, side, n, scale, attention_impl):
-    if attention_impl == 2 and side > 240:
+    if attention_impl >= 2 and side > 240:
         pytest.skip("tcgen05 attention covers frames of <= 256 tokens")
     model = oenc.build_hf_model(arch, seed=0, init_scale=scale)
     frames = oenc.synthetic_frames(n, side, side, seed=5)

@@ -67,6 +67,23 @@ def test_attention_tcgen05(side, heads, frames):
     assert e < 1.5e-2, f"tcgen05 attention rel err {e}"
 
 
+@pytest.mark.parametrize("side,heads,frames", [(224, 12, 3), (224, 6, 37), (64, 12, 5), (240, 16, 2)])
+def test_attention_tcgen05_rope_prologue(side, heads, frames):
+    n = side // 16
+    T, P, D = n * n + 5, 5, heads * 64
+    cos, sin = rope_tables(n, n)
+    cos, sin = cos.cuda(), sin.cuda()
+    qkv = (torch.randn(frames * T, 3 * D, device="cuda") * 1.5).to(torch.bfloat16)
+    out = attention_tc(qkv, frames, T, heads, cos, sin, P).float()
+    x = qkv.float().view(frames, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    q, k = _rope_ref(x[0], x[1], cos, sin)
+    want = F.scaled_dot_product_attention(q, k, x[2], scale=0.125).permute(0, 2, 1, 3).reshape(frames * T, D)
+    e = rel_err(out, want)
+    assert e < 1.5e-2, f"tcgen05 attention + RoPE prologue rel err {e}"
+    legacy = attention(qkv, cos, sin, frames, T, P, heads).float()  # the mma.sync kernel does the same job
+    assert rel_err(out, legacy) < 1.5e-2
+
+
 def test_qkv_gemm_rope_epilogue():
     n, heads, frames, P = 14, 6, 5, 5
     T, D = n * n + P, heads * 64
