@@ -76,14 +76,13 @@ SIGNATURES = {
                                                  c_void_p]),
     "cbas_b200_gemm_bf16": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                       c_void_p]),
+    "cbas_b200_debug_resize_tiled": (C.c_int, [c_int32]),
     "cbas_b200_debug_gemm_cta_group": (C.c_int, [c_int32]),
     "cbas_b200_layernorm": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
     "cbas_b200_attention": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                       c_void_p]),
     "cbas_b200_attention_tc": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                          c_void_p]),
-    "cbas_b200_gemm_qkv_rope": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
-                                          c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "cbas_b200_debug_attention_impl": (C.c_int, [c_int32]),
     "cbas_b200_preprocess_green": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_int32,
                                              c_void_p]),

@@ -6,10 +6,12 @@
 //   tcgen05  : S_mt = Q_mt K^T  (128 x TK x 64, fp32 in TMEM) for both query tiles;
 //              O_mt = P_mt V    (128 x 64 x TK) with P read FROM TMEM (bf16 written over S by the softmax
 //              warps) and V consumed MN-major exactly as TMA laid it down - no transposes, no P in smem.
-//   softmax  : two warpgroups, one per query tile; a thread owns one query row, so the row max / sum need no
-//              shuffles: pass 1 reads S for the max, pass 2 re-reads S, exponentiates (exp2, scale folded),
-//              packs bf16 pairs and stores them over the columns of S already consumed.
-//   epilogue : O / rowsum -> bf16 -> [M, D] at column head*64, a full 128-byte line per thread.
+//   softmax  : four warpgroups, two per query tile; a thread owns one query row and HALF of its keys (TMEM lane
+//              access is tied to warp_id % 4, so two warps share each lane quarter).  Pass 1 reads S for the
+//              partial row max (exchanged with the partner thread through shared memory), pass 2 re-reads S,
+//              exponentiates (exp2, scale folded), packs bf16 pairs and stores them over consumed columns of S.
+//   epilogue : each of the two threads of a row scales 32 of the 64 output columns by 1 / (sum_a + sum_b)
+//              -> bf16 -> [M, D] at column head*64.
 //
 //   RoPE     : attention prologue, in shared memory.  While the tensor core runs PV of item i, the softmax warps
 //              rotate the Q and K rows of item i+1 in place (rotate-half form, fp32 math, cos/sin held as
@@ -17,15 +19,21 @@
 //              async proxy and release the MMA warp through an mbarrier.  Rows of prefix tokens and rows past
 //              the frame are left alone.  (Pass null tables to skip RoPE, e.g. when the QKV epilogue did it.)
 //
-// TMEM map (512 columns): query tile mt owns columns [256*mt, 256*mt+256): S at +0..TK, P (bf16 pairs) at
-// +0..TK/2, O at +192..+256 (written only after the softmax has consumed S, read back by the same warps).
+// TMEM map (512 columns): query tile mt owns columns [256*mt, 256*mt+256): S at +0..TK; P (bf16 pairs) of the
+// first key half at +0..CA/2 and of the second half at +CA..+CA+(TK-CA)/2; O at +192..+256 (written only after
+// the softmax has consumed S, read back by the same warps).
 // Reference semantics: HF modeling_dinov3_vit.py:316-329 (SDPA, scale 1/8, no mask, non-causal).
 #pragma once
 #include "ptx.cuh"
 
 namespace cbas {
 
-constexpr int ATC_THREADS = 384;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 softmax tile 0, 8-11 softmax tile 1
+// warps 0-7 softmax/epilogue of query tile 0 (0-3 first half of the keys, 4-7 second half), 8-15 of tile 1; then
+// (highest ids = highest issue priority) warp 16 TMA producer, 17 MMA issuer, 18 TMEM allocator, 19 idle
+constexpr int ATC_THREADS = 640;
+constexpr int ATC_SOFTMAX_WARPS = 16;
+constexpr int ATC_PRODUCER_WARP = 16, ATC_MMA_WARP = 17, ATC_ALLOC_WARP = 18;
+constexpr int ATC_XCHG_BYTES = 2 * 2 * 2 * 128 * 4;  // [max|sum][tile][half][row] floats
 constexpr int ATC_O_COL = 192;
 
 struct AttnTcParams {
@@ -41,7 +49,7 @@ struct AttnTcParams {
 __host__ __device__ inline int atc_set_bytes(int TK) { return 2 * 128 * 128 + 2 * TK * 128; }
 __host__ __device__ inline int atc_rope_bytes(int T, int prefix) { return ((T - prefix) * 32 * 4 + 127) & ~127; }
 __host__ __device__ inline int atc_smem_bytes(int TK, int T, int prefix, bool rope) {
-    return 2 * atc_set_bytes(TK) + (rope ? atc_rope_bytes(T, prefix) : 0) + 1024 + 256;
+    return 2 * atc_set_bytes(TK) + (rope ? atc_rope_bytes(T, prefix) : 0) + ATC_XCHG_BYTES + 1024 + 256;
 }
 
 // Rotate the patch-token rows of one [rows,64] bf16 tile in place.  `u` enumerates (row, chunk pair): a warp
@@ -80,7 +88,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
     const int set_bytes = atc_set_bytes(TK);
     const bool rope = p.rope_cos != nullptr;
     __half2* rope_tab = reinterpret_cast<__half2*>(smem + 2 * set_bytes);  // [T - prefix][32] (cos, sin)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * set_bytes + (rope ? atc_rope_bytes(T, p.prefix) : 0));
+    float* xchg = reinterpret_cast<float*>(smem + 2 * set_bytes + (rope ? atc_rope_bytes(T, p.prefix) : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + ATC_XCHG_BYTES);
     uint64_t* kv_full = bars;        // [2] TMA -> (softmax warps, then) MMA
     uint64_t* kv_empty = bars + 2;   // [2] MMA -> TMA
     uint64_t* s_full = bars + 4;     // [2] per query tile: MMA -> softmax
@@ -93,19 +102,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_items = p.frames * p.heads;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == ATC_PRODUCER_WARP && lane == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_kv);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == ATC_MMA_WARP && lane == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&kv_full[i], 1);
             mbar_init(&kv_empty[i], 1);
             mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 4);
+            mbar_init(&p_full[i], 8);
             mbar_init(&o_full[i], 1);
-            mbar_init(&o_empty[i], 4);
-            mbar_init(&qk_ready[i], 8);
+            mbar_init(&o_empty[i], 8);
+            mbar_init(&qk_ready[i], ATC_SOFTMAX_WARPS);
         }
         fence_mbar_init();
     }
@@ -114,7 +123,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
         for (int i = threadIdx.x; i < n; i += blockDim.x)
             rope_tab[i] = __floats2half2_rn(__ldg(p.rope_cos + i), __ldg(p.rope_sin + i));
     }
-    if (warp == 2) {
+    if (warp == ATC_ALLOC_WARP) {
         tmem_alloc(tmem_ptr_smem, 512);
         tmem_relinquish();
     }
@@ -123,7 +132,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == 0) {
+    if (warp == ATC_PRODUCER_WARP) {
         if (lane == 0) {
             // ---------------------------------------------------------------- TMA producer
             int it = 0;
@@ -140,7 +149,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                 tma_load_2d(set + 32768 + TK * 128, &tmap_kv, &kv_full[b], 2 * p.D + h * 64, row0);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == ATC_MMA_WARP) {
         if (lane == 0) {
             // ---------------------------------------------------------------- MMA issuer
             const uint32_t idesc_s = umma_idesc_bf16(128, TK);
@@ -167,33 +176,46 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                 for (int mt = 0; mt < 2; ++mt) {
                     mbar_wait(&p_full[mt], it & 1);
                     tc_fence_after();
-                    for (int k = 0; k < TK / 16; ++k)  // 16 keys per MMA: 8 TMEM columns of P, 2048 B of V
-                        umma_bf16_ts(tmem_base + 256 * mt + ATC_O_COL, tmem_base + 256 * mt + 8 * k, dv + 128 * k,
+                    const int ka = (((TK >> 4) + 1) / 2);  // k-steps whose keys belong to the first half of the row
+                    for (int k = 0; k < TK / 16; ++k) {    // 16 keys per MMA: 8 TMEM columns of P, 2048 B of V
+                        // P of keys [0,CA) sits at columns [0,CA/2); P of keys [CA,TK) at [CA, CA+(TK-CA)/2): each
+                        // softmax thread overwrites only columns of S that it has itself already consumed
+                        const int pcol = k < ka ? 8 * k : 16 * ka + 8 * (k - ka);
+                        umma_bf16_ts(tmem_base + 256 * mt + ATC_O_COL, tmem_base + 256 * mt + pcol, dv + 128 * k,
                                      idesc_o, k != 0);
+                    }
                     umma_commit(&o_full[mt]);
                 }
                 umma_commit(&kv_empty[b]);  // every MMA that reads this shared-memory set has retired
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < ATC_SOFTMAX_WARPS) {
         // ------------------------------------------------------------------- softmax + epilogue warpgroups
-        const int mt = (warp - 4) >> 2;
+        const int mt = warp >> 3;          // query tile
+        const int half = (warp >> 2) & 1;  // which half of the keys (and of the output columns)
         const int quarter = warp & 3;
-        const int row = mt * 128 + quarter * 32 + lane;  // query token inside the frame
+        const int rit = quarter * 32 + lane;      // row inside the tile
+        const int row = mt * 128 + rit;           // query token inside the frame
         const bool warp_has_rows = (mt * 128 + quarter * 32) < T;
         const uint32_t t_row = tmem_base + 256 * mt + (uint32_t(quarter * 32) << 16);
         const float c = p.scale_log2;
-        const int wtid = threadIdx.x - 128;  // 0..255 over both softmax warpgroups
+        const int CA = ((TK >> 4) + 1) / 2 * 16;  // keys [0,CA) for half 0, [CA,TK) for half 1 (multiples of 16)
+        const int c_begin = half ? CA : 0, c_end = half ? TK : CA;
+        float* my_max = xchg + ((0 * 2 + mt) * 2 + half) * 128 + rit;
+        float* peer_max = xchg + ((0 * 2 + mt) * 2 + (half ^ 1)) * 128 + rit;
+        float* my_sum = xchg + ((1 * 2 + mt) * 2 + half) * 128 + rit;
+        float* peer_sum = xchg + ((1 * 2 + mt) * 2 + (half ^ 1)) * 128 + rit;
+        const int wtid = threadIdx.x;  // 0..511 over the softmax warps
         // rotate Q (256 rows in two tiles) and K (TK rows) of the item that sits in buffer set `b`
         auto rotate_set = [&](int b, int iter) {
             mbar_wait(&kv_full[b], (iter >> 1) & 1);
             uint8_t* set = smem + b * set_bytes;
             const int units = (256 + TK) * 4;
-            for (int u = wtid; u < units; u += 256) {
-                const int row = u >> 2, cpair = u & 3;
-                const int tok = row < 256 ? row : row - 256;
+            for (int u = wtid; u < units; u += ATC_SOFTMAX_WARPS * 32) {
+                const int r = u >> 2, cpair = u & 3;
+                const int tok = r < 256 ? r : r - 256;
                 if (tok >= p.prefix && tok < T)
-                    atc_rope_unit(row < 256 ? set : set + 32768 - 256 * 128, row, cpair, rope_tab + (tok - p.prefix) * 32);
+                    atc_rope_unit(r < 256 ? set : set + 32768 - 256 * 128, r, cpair, rope_tab + (tok - p.prefix) * 32);
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
             __syncwarp();
@@ -205,46 +227,40 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             const int f = w / p.heads, h = w % p.heads;
             mbar_wait(&s_full[mt], it & 1);
             tc_fence_after();
-            float inv_sum = 0.f;
+            float sum = 0.f;
+            // pass 1: partial row max over this thread's valid keys
+            float mx = -INFINITY;
             if (warp_has_rows) {
-                // pass 1: row max over the T valid keys
-                float mx = -INFINITY;
-                for (int c0 = 0; c0 < TK; c0 += 32) {
-                    if (c0 + 32 <= T) {  // chunk entirely inside the frame: no masking
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_row + c0, v);
-                        tmem_ld_wait();
+                for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(t_row + c0, v);
+                    tmem_ld_wait();
+                    if (c0 + 16 <= T) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2)
+                        for (int j = 0; j < 16; j += 2)
                             mx = fmaxf(mx, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
-                    } else if (c0 + 32 <= TK) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_row + c0, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
                     } else {
-                        uint32_t v[16];
-                        tmem_ld_32x16(t_row + c0, v);
-                        tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
                     }
                 }
+            }
+            *my_max = mx;
+            named_bar_sync(1 + mt, 256);  // the two warpgroups of this query tile
+            if (warp_has_rows) {
+                mx = fmaxf(mx, *peer_max);
                 const float mc = mx * c;
-                // pass 2: p = exp2(s*c - max*c), row sum, bf16 pairs written over the consumed part of S
-                float sum = 0.f;
-                for (int c0 = 0; c0 < TK; c0 += 32) {
-                    if (c0 + 32 <= T) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_row + c0, v);
-                        tmem_ld_wait();
-                        uint32_t pk[16];
+                // pass 2: p = exp2(s*c - max*c), partial row sum, bf16 pairs written over the consumed part of S
+                for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(t_row + c0, v);
+                    tmem_ld_wait();
+                    uint32_t pk[8];
+                    if (c0 + 16 <= T) {
                         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
+                        for (int j = 0; j < 16; j += 2) {
                             const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), c, -mc));
                             const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), c, -mc));
                             s0 += e0;
@@ -252,25 +268,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                             pk[j >> 1] = pack_bf16(e0, e1);
                         }
                         sum += s0 + s1;
-                        tmem_st_32x16(t_row + (c0 >> 1), pk);
-                    } else if (c0 + 32 <= TK) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_row + c0, v);
-                        tmem_ld_wait();
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const float e0 = (c0 + j < T) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -mc)) : 0.f;
-                            const float e1 = (c0 + j + 1 < T) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), c, -mc)) : 0.f;
-                            sum += e0 + e1;
-                            pk[j >> 1] = pack_bf16(e0, e1);
-                        }
-                        tmem_st_32x16(t_row + (c0 >> 1), pk);
                     } else {
-                        uint32_t v[16];
-                        tmem_ld_32x16(t_row + c0, v);
-                        tmem_ld_wait();
-                        uint32_t pk[8];
 #pragma unroll
                         for (int j = 0; j < 16; j += 2) {
                             const float e0 = (c0 + j < T) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -mc)) : 0.f;
@@ -278,12 +276,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                             sum += e0 + e1;
                             pk[j >> 1] = pack_bf16(e0, e1);
                         }
-                        tmem_st_32x8(t_row + (c0 >> 1), pk);
                     }
+                    tmem_st_32x8(t_row + c_begin + ((c0 - c_begin) >> 1), pk);
                 }
                 tmem_st_wait();
-                inv_sum = 1.0f / sum;
             }
+            *my_sum = sum;  // read by the partner thread after o_full (ordered through the mbarrier chain)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[mt]);
@@ -294,12 +292,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             mbar_wait(&o_full[mt], it & 1);
             tc_fence_after();
             if (warp_has_rows) {
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32(t_row + ATC_O_COL, v0);
-                tmem_ld_32x32(t_row + ATC_O_COL + 32, v1);
+                uint32_t v0[32];
+                tmem_ld_32x32(t_row + ATC_O_COL + 32 * half, v0);
                 tmem_ld_wait();
+                // read the partner's partial sum BEFORE releasing the tile: once o_empty completes the partner may
+                // run ahead into the next item and overwrite it
+                const float inv_sum = 1.0f / (sum + *peer_sum);
+                // O is in registers: hand the TMEM half back before the global stores
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&o_empty[mt]);
                 if (row < T) {
-                    __nv_bfloat16* o = p.out + ((long long)f * T + row) * p.D + h * 64;
+                    __nv_bfloat16* o = p.out + ((long long)f * T + row) * p.D + h * 64 + 32 * half;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         uint4 q;
@@ -309,27 +313,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                         q.w = pack_bf16(__uint_as_float(v0[j + 6]) * inv_sum, __uint_as_float(v0[j + 7]) * inv_sum);
                         *reinterpret_cast<uint4*>(o + j) = q;
                     }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 q;
-                        q.x = pack_bf16(__uint_as_float(v1[j]) * inv_sum, __uint_as_float(v1[j + 1]) * inv_sum);
-                        q.y = pack_bf16(__uint_as_float(v1[j + 2]) * inv_sum, __uint_as_float(v1[j + 3]) * inv_sum);
-                        q.z = pack_bf16(__uint_as_float(v1[j + 4]) * inv_sum, __uint_as_float(v1[j + 5]) * inv_sum);
-                        q.w = pack_bf16(__uint_as_float(v1[j + 6]) * inv_sum, __uint_as_float(v1[j + 7]) * inv_sum);
-                        *reinterpret_cast<uint4*>(o + 32 + j) = q;
-                    }
                 }
+            } else {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&o_empty[mt]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&o_empty[mt]);
         }
     }
 
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == ATC_ALLOC_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }

@@ -77,10 +77,16 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* 
     return check_cuda(cudaGetLastError(), "attention_kernel launch");
 }
 
-int g_attention_impl = 0;  // 0 auto (tcgen05 when T <= 256), 1 mma.sync + RoPE prologue, 2 tcgen05, 3 tcgen05 + epilogue RoPE
-bool g_rope_in_epilogue = false;
+bool g_resize_tiled = true;  // false: per-pixel kernel (test knob)
+int g_attention_impl = 0;  // 0 auto (tcgen05 when T <= 256), 1 mma.sync, 2 tcgen05 (both rotate q,k in their prologue)
 
-bool use_attention_tc(int T) { return g_attention_impl >= 2 || (g_attention_impl == 0 && T <= 256); }
+bool attention_tc_fits(int T, int prefix) {
+    const int TK = (T + 15) & ~15;
+    return TK <= 256 && atc_smem_bytes(TK, T, prefix, true) <= 232448;
+}
+bool use_attention_tc(int T, int prefix) {
+    return g_attention_impl >= 2 || (g_attention_impl == 0 && attention_tc_fits(T, prefix));
+}
 
 // cs/sn: RoPE tables applied in the kernel's prologue, or null when q and k arrive rotated (EPI_QKV_ROPE_BF16)
 int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* cs, const float* sn, int frames,
@@ -133,6 +139,23 @@ int launch_preprocess_resize(const uint8_t* frames, __nv_bfloat16* A, int n, int
     // ImageNet mean/std (transformers image_utils.IMAGENET_DEFAULT_MEAN / _STD)
     const float3 mean = make_float3(0.485f, 0.456f, 0.406f);
     const float3 istd = make_float3(1.0f / 0.229f, 1.0f / 0.224f, 1.0f / 0.225f);
+    // tiled shared-memory path when the geometry allows it: 16-byte aligned rows, strip fits in shared memory
+    const int max_rows = (int)((16LL * H + side - 1) / side) + tp.taps_y + 1;
+    const int src_pitch = (W * 3 + 15) & ~15;
+    const size_t tile_smem = (size_t)max_rows * src_pitch + (size_t)max_rows * side * 3 * 4;
+    if (g_resize_tiled && tile_smem <= 200 * 1024 && (reinterpret_cast<uintptr_t>(frames) & 15) == 0 && fs % 16 == 0 &&
+        rs % 16 == 0) {
+        static size_t configured = 0;
+        if (tile_smem > configured) {
+            CBAS_CHECK(cudaFuncSetAttribute(preprocess_resize_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)tile_smem));
+            configured = tile_smem;
+        }
+        preprocess_resize_tile_kernel<<<n * (side / 16), 256, tile_smem, s>>>(frames, A, H, W, fs, rs, side, tp, mean,
+                                                                             istd, max_rows);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "preprocess_resize_tile_kernel launch");
+    }
     preprocess_resize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(frames, A, n, H, W, fs, rs, side, tp, mean,
                                                                             istd);
     count_launch();
@@ -197,14 +220,7 @@ int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
                                                  c.ln_eps, s)) return rc;
     GemmParams p{};
     p.M = M; p.N = 3 * D; p.K = D; p.bias = (const float*)L.b_qkv; p.out = e->qkv; p.ldo = 3 * D;
-    if (use_attention_tc(e->T) && g_rope_in_epilogue) {
-        // RoPE on the fp32 accumulators in the QKV epilogue, then the tcgen05 attention kernel
-        p.rows_out = e->T; p.prefix = c.prefix_tokens; p.rope_cols = 2 * D;
-        p.rope_cos = (const float*)e->w.rope_cos; p.rope_sin = (const float*)e->w.rope_sin;
-        if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_QKV_ROPE_BF16, s, PROF_QKV_GEMM))
-            return rc;
-        if (int rc = launch_attention_tc(e->qkv, e->xn, nullptr, nullptr, n, e->T, c.prefix_tokens, c.heads, s)) return rc;
-    } else if (use_attention_tc(e->T)) {
+    if (use_attention_tc(e->T, c.prefix_tokens)) {
         // plain QKV projection; the tcgen05 attention kernel rotates q and k in its prologue
         if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16, s, PROF_QKV_GEMM))
             return rc;
@@ -324,10 +340,8 @@ int cbas_b200_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_
 }
 
 int cbas_b200_debug_attention_impl(int32_t impl) {
-    if (impl < 0 || impl > 3)
-        return fail("attention impl must be 0 (auto), 1 (mma.sync), 2 (tcgen05) or 3 (tcgen05, RoPE in the QKV epilogue)");
+    if (impl < 0 || impl > 2) return fail("attention impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
     g_attention_impl = impl;
-    g_rope_in_epilogue = impl == 3;
     return 0;
 }
 
@@ -338,15 +352,9 @@ int cbas_b200_attention_tc(const void* qkv_bf16_dev, void* out_bf16_dev, const f
                                rope_sin_dev, frames, T, prefix, heads, (cudaStream_t)stream);
 }
 
-int cbas_b200_gemm_qkv_rope(const void* a_dev, const void* w_dev, const float* bias_dev, void* out_bf16_dev,
-                            int32_t M, int32_t N, int32_t K, const float* rope_cos_dev, const float* rope_sin_dev,
-                            int32_t T, int32_t prefix, int32_t rope_cols, void* stream) {
-    GemmParams p{};
-    p.M = M; p.N = N; p.K = K; p.bias = bias_dev; p.out = out_bf16_dev; p.ldo = N;
-    p.rows_out = T; p.prefix = prefix; p.rope_cols = rope_cols; p.rope_cos = rope_cos_dev; p.rope_sin = rope_sin_dev;
-    if (N % 64 || rope_cols % 64) return fail("head slices are 64 columns wide");
-    return launch_gemm((const __nv_bfloat16*)a_dev, K, (const __nv_bfloat16*)w_dev, K, p, EPI_QKV_ROPE_BF16,
-                       (cudaStream_t)stream);
+int cbas_b200_debug_resize_tiled(int32_t on) {
+    g_resize_tiled = on != 0;
+    return 0;
 }
 
 int cbas_b200_debug_gemm_cta_group(int32_t cg) {

@@ -48,7 +48,7 @@ int make_tmap(CUtensorMap* map, const void* base, bool f32, int rows, int cols, 
 
 template <int BLOCK_N, int EPI, int CG>
 int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-    using Cfg = GemmCfg<BLOCK_N, CG>;
+    using Cfg = GemmCfg<BLOCK_N, CG, gemm_epi_double_stage(EPI)>;
     auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI, CG>;
     static bool configured = false;  // per instantiation
     if (!configured) {
@@ -97,7 +97,6 @@ int launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
         case EPI_PATCH_F32: return launch_one<BLOCK_N, EPI_PATCH_F32, CG>(ta, tb, p, stream);
         case EPI_BIAS_F32: return launch_one<BLOCK_N, EPI_BIAS_F32, CG>(ta, tb, p, stream);
         case EPI_BIAS_GELU_F32: return launch_one<BLOCK_N, EPI_BIAS_GELU_F32, CG>(ta, tb, p, stream);
-        case EPI_QKV_ROPE_BF16: return launch_one<BLOCK_N, EPI_QKV_ROPE_BF16, CG>(ta, tb, p, stream);
     }
     return fail("unknown GEMM epilogue " + std::to_string(epi));
 }

@@ -5,14 +5,18 @@
 //   accumulators in TMEM, double-buffered) -> tcgen05.ld -> epilogue math in registers -> swizzled
 //   shared-memory slab -> TMA store (or TMA add-reduction into the fp32 residual stream) -> global.
 //
-// Warp roles (one CTA per SM, 128 + 256 threads):
-//   warp 0   : TMA producer (one elected lane)
-//   warp 1   : MMA issuer   (one elected lane)
-//   warp 2   : TMEM allocator / deallocator
-//   warp 3   : idle
-//   warps 4-11: epilogue, two groups of four warps (warp w reads TMEM lanes 32*(w%4)..+31, the only ones it
-//              may touch).  A group owns one 16 KB staging slab (128 rows x 128 B) and walks the tile's column
-//              slabs g, g+2, ...; one thread per group issues the bulk tensor stores.
+// Warp roles (one CTA per SM, 512 + 128 threads).  The single-thread roles sit in the HIGHEST warp ids: the warp
+// scheduler favours higher warp ids among ready warps, so the TMA/MMA issue threads are never starved by sixteen
+// epilogue warps crunching GELU in the same sub-partitions.
+//   warp 16  : TMA producer (one elected lane)
+//   warp 17  : MMA issuer   (one elected lane)
+//   warp 18  : TMEM allocator / deallocator
+//   warp 19  : idle
+//   warps 0-15: epilogue, two groups of eight warps.  Warp w may only read TMEM lanes 32*(w%4)..+31, so a group
+//              has two warps per lane quarter and each takes half of the slab's columns (64 B of every row).
+//              A group owns one 16 KB staging slab (128 rows x 128 B) and walks the tile's column slabs
+//              g, g+2, ...; one thread per group issues the bulk tensor stores.  Four epilogue warps per SM
+//              sub-partition keep the TMEM-load / MUFU / store latencies of the K=768 GEMMs under the MMA time.
 //
 // The epilogues are the ones the DINOv3 block needs (reference: HF modeling_dinov3_vit.py:305-311 QKV bias,
 // :385-386 up_proj+GELU, :440-441 / :447-448 LayerScale+residual (LayerScale is folded into W and bias on
@@ -31,7 +35,6 @@ enum GemmEpilogue : int {
     EPI_PATCH_F32 = 3,       // resid_f32[row_map(m),n] = acc + bias[n]  (patch rows behind the prefix tokens)
     EPI_BIAS_F32 = 4,        // out_f32[m,n] = acc + bias[n]
     EPI_BIAS_GELU_F32 = 5,   // out_f32[m,n] = gelu_erf(acc + bias[n])
-    EPI_QKV_ROPE_BF16 = 6,   // EPI_BIAS_BF16 + DINOv3 RoPE on the q and k head slices of patch tokens
 };
 
 struct GemmParams {
@@ -41,37 +44,34 @@ struct GemmParams {
     int ldo;
     // EPI_PATCH_F32: A row m = frame*rows_in + p  ->  out row frame*rows_out + prefix + p
     int rows_in, rows_out, prefix;
-    // EPI_QKV_ROPE_BF16 (HF modeling_dinov3_vit.py:238-268): row m is token m % rows_out of its frame; tokens >=
-    // prefix are rotated in every 64-wide head slice of columns [0, rope_cols) (= the q and k thirds), on the
-    // fp32 accumulators:  x1' = x1 cos - x2 sin,  x2' = x2 cos + x1 sin,  tables [rows_out - prefix, 32] fp32.
-    const float* rope_cos;
-    const float* rope_sin;
-    int rope_cols;
 };
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_UMMA_K = 16;
-constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_EPI_WARPS = 16;
 constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_SLAB_BYTES = GEMM_BLOCK_M * 128;  // 128 rows x 128 B
 
-__host__ __device__ constexpr bool gemm_epi_out_bf16(int epi) {
-    return epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_QKV_ROPE_BF16;
-}
+__host__ __device__ constexpr bool gemm_epi_out_bf16(int epi) { return epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16; }
 __host__ __device__ constexpr bool gemm_epi_staged(int epi) { return epi != EPI_PATCH_F32; }
+__host__ __device__ constexpr bool gemm_epi_double_stage(int epi) { return epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_GELU_F32; }
 __host__ __device__ constexpr int gemm_slab_cols(int epi) { return gemm_epi_out_bf16(epi) ? 64 : 32; }
 
 // CG = 1: one CTA computes a 128 x BLOCK_N tile.  CG = 2: a CTA pair (cluster of two SMs, tcgen05 cta_group::2)
 // computes a 256 x BLOCK_N tile; each CTA loads its own 128 A rows but only HALF of the B rows, which cuts the
 // L2 -> shared-memory operand traffic per FLOP by a third - the 1-CTA mainloop is bound by exactly that traffic.
-template <int BLOCK_N, int CG = 1>
+// kDoubleStage: two staging slabs per epilogue group (the bulk store of slab s overlaps the math of slab s+1) at
+// the price of one mainloop stage - worth it only for the ALU-heavy GELU epilogues.
+template <int BLOCK_N, int CG = 1, bool kDoubleStage = false>
 struct GemmCfg {
     static constexpr int kStageA = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;  // 16 KB
     static constexpr int kStageB = (BLOCK_N / CG) * GEMM_BLOCK_K * 2;
     static constexpr int kStage = kStageA + kStageB;
-    static constexpr int kStaging = 2 * GEMM_SLAB_BYTES;  // one slab per epilogue group
-    static constexpr int kStages = (192 * 1024) / kStage > 8 ? 8 : (192 * 1024) / kStage;
+    static constexpr int kSlabsPerGroup = kDoubleStage ? 2 : 1;
+    static constexpr int kStaging = 2 * kSlabsPerGroup * GEMM_SLAB_BYTES;
+    static constexpr int kBudget = 232448 - 1024 - 256 - kStaging;
+    static constexpr int kStages = kBudget / kStage > 8 ? 8 : kBudget / kStage;
     static constexpr int kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;
     static constexpr int kSmemBytes = kStages * kStage + kStaging + 1024 /*align slack*/ + 256 /*barriers*/;
     static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -81,7 +81,7 @@ template <int BLOCK_N, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
-    using Cfg = GemmCfg<BLOCK_N, CG>;
+    using Cfg = GemmCfg<BLOCK_N, CG, gemm_epi_double_stage(EPI)>;
     static_assert(CG == 1 || CG == 2, "cta_group");
     static_assert((BLOCK_N / CG) % 8 == 0 && BLOCK_N % 16 == 0, "UMMA N");
     constexpr int kStages = Cfg::kStages;
@@ -97,7 +97,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Cfg::kStageA;
-    uint8_t* smem_stage = smem + kStages * Cfg::kStage;  // 2 x 16 KB, 1024-aligned
+    uint8_t* smem_stage = smem + kStages * Cfg::kStage;  // 4 x 16 KB, 1024-aligned
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + Cfg::kStaging);
     uint64_t* full_bar = bars;                      // [kStages] TMA -> MMA
     uint64_t* empty_bar = bars + kStages;           // [kStages] MMA -> TMA
@@ -117,12 +117,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
     if (CG == 2) cluster_sync_all();  // both CTAs resident before the pair-wide TMEM allocation
-    if (warp == 0 && lane == 0) {
+    constexpr int kProducerWarp = GEMM_EPI_WARPS, kMmaWarp = GEMM_EPI_WARPS + 1, kAllocWarp = GEMM_EPI_WARPS + 2;
+    if (warp == kProducerWarp && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         if (kStaged) tma_prefetch_desc(&tmap_out);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == kMmaWarp && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], CG);  // pair: one arrival per CTA, all on the leader's barrier
             mbar_init(&empty_bar[i], 1);
@@ -133,7 +134,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         fence_mbar_init();
     }
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         if (CG == 2) { tmem_alloc_pair(tmem_ptr_smem, Cfg::kTmemCols); tmem_relinquish_pair(); }
         else { tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols); tmem_relinquish(); }
     }
@@ -142,7 +143,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == 0) {
+    if (warp == kProducerWarp) {
         if (lane == 0) {
             // ------------------------------------------------------------ TMA producer
             uint32_t stage = 0, phase = 0;
@@ -169,7 +170,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         if (lane == 0 && cta_rank == 0) {
             // ------------------------------------------------------------ MMA issuer (pair: leader CTA only)
             constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BLOCK_N);
@@ -200,16 +201,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < GEMM_EPI_WARPS) {
         // ---------------------------------------------------------------- epilogue
-        const int ew = warp - 4;
-        const int group = ew >> 2;     // 0 or 1
-        const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+        const int ew = warp;               // 0..15
+        const int group = ew >> 3;         // 0 or 1: which staging slab / which slabs of the tile
+        const int sub = (ew >> 2) & 1;     // which half of a slab's columns
+        const int quarter = warp & 3;      // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
         const int row_in_tile = quarter * 32 + lane;
-        const bool issuer = (ew & 3) == 0 && lane == 0;  // one bulk-store issuer per group
-        uint8_t* slab = smem_stage + group * GEMM_SLAB_BYTES;
-        uint8_t* slab_row = slab + row_in_tile * 128;
+        const bool issuer = (ew & 7) == 0 && lane == 0;  // one bulk-store issuer per group
+        constexpr int kHalf = kSlabCols / 2;             // columns per thread per slab: 32 (bf16) or 16 (fp32)
+        uint8_t* group_slabs = smem_stage + group * Cfg::kSlabsPerGroup * GEMM_SLAB_BYTES;
         const int swz = row_in_tile & 7;
+        uint32_t sbuf = 0;  // which of the group's two staging slabs the next slab uses
         int iter = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++iter) {
             const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
@@ -222,16 +225,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if constexpr (kStaged) {
 #pragma unroll 1
                 for (int s = group; s < kSlabs; s += 2) {
-                    const int c0 = s * kSlabCols;         // column inside the tile
-                    const int n0 = n_blk * BLOCK_N + c0;  // global column
-                    float x[kSlabCols];
-#pragma unroll
-                    for (int c = 0; c < kSlabCols; c += 32) {
+                    const int c0 = s * kSlabCols + sub * kHalf;  // this thread's first column inside the tile
+                    const int n0 = n_blk * BLOCK_N + c0;         // ... and in the matrix
+                    float x[kHalf];
+                    if constexpr (kHalf == 32) {
                         uint32_t v[32];
-                        tmem_ld_32x32(taddr_row + c0 + c, v);
+                        tmem_ld_32x32(taddr_row + c0, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) x[c + j] = __uint_as_float(v[j]);
+                        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+                    } else {
+                        uint32_t v[16];
+                        tmem_ld_32x16(taddr_row + c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
                     }
                     if (s + 2 >= kSlabs) {
                         // last slab of this tile for this warp: the accumulator can go back to the MMA warp
@@ -243,39 +251,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                     if (p.bias) {
 #pragma unroll
-                        for (int j = 0; j < kSlabCols; j += 4) {
+                        for (int j = 0; j < kHalf; j += 4) {
                             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
                             x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
                         }
                     }
-                    if constexpr (EPI == EPI_QKV_ROPE_BF16) {
-                        // one slab = one head slice (64 columns): both rotation halves sit in this thread
-                        const int tok = (m_base + row_in_tile) % p.rows_out;
-                        if (n0 < p.rope_cols && tok >= p.prefix) {
-                            const float4* cs = reinterpret_cast<const float4*>(p.rope_cos + (tok - p.prefix) * 32);
-                            const float4* sn = reinterpret_cast<const float4*>(p.rope_sin + (tok - p.prefix) * 32);
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 c4 = __ldg(cs + (j >> 2)), s4 = __ldg(sn + (j >> 2));
-                                const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float a = x[j + e], b = x[32 + j + e];
-                                    x[j + e] = a * cc[e] - b * ss[e];
-                                    x[32 + j + e] = b * cc[e] + a * ss[e];
-                                }
-                            }
-                        }
-                    }
                     if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_F32) {
 #pragma unroll
-                        for (int j = 0; j < kSlabCols; ++j) x[j] = gelu_erf_fast(x[j]);
+                        for (int j = 0; j < kHalf; ++j) x[j] = gelu_erf_fast(x[j]);
                     }
-                    // the group's previous bulk store must have finished reading the slab
-                    if (issuer) tma_wait_group_read<0>();
-                    named_bar_sync(1 + group, 128);
+                    // the bulk store issued from THIS slab buffer two slabs ago must have finished reading it
+                    uint8_t* slab = group_slabs + sbuf * GEMM_SLAB_BYTES;
+                    uint8_t* slab_row = slab + row_in_tile * 128;
+                    if (Cfg::kSlabsPerGroup == 2) {
+                        sbuf ^= 1;
+                        if (issuer) tma_wait_group_read<1>();
+                    } else {
+                        if (issuer) tma_wait_group_read<0>();
+                    }
+                    named_bar_sync(1 + group, 256);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {  // 8 x 16-byte chunks per 128-byte row, XOR-swizzled like TMA
+                    for (int j = 0; j < 4; ++j) {  // this thread's 4 of the row's 8 16-byte chunks, XOR-swizzled like TMA
                         uint4 q;
                         if constexpr (kOutBf16) {
                             q.x = pack_bf16(x[8 * j + 0], x[8 * j + 1]);
@@ -288,34 +284,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             q.z = __float_as_uint(x[4 * j + 2]);
                             q.w = __float_as_uint(x[4 * j + 3]);
                         }
-                        *reinterpret_cast<uint4*>(slab_row + ((j ^ swz) << 4)) = q;
+                        *reinterpret_cast<uint4*>(slab_row + (((sub * 4 + j) ^ swz) << 4)) = q;
                     }
                     fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
-                    named_bar_sync(1 + group, 128);
+                    named_bar_sync(1 + group, 256);
                     if (issuer) {
-                        if (EPI == EPI_RESID_F32) tma_reduce_add_2d(&tmap_out, slab, n0, m_base);
-                        else tma_store_2d(&tmap_out, slab, n0, m_base);
+                        const int ns = n_blk * BLOCK_N + s * kSlabCols;
+                        if (EPI == EPI_RESID_F32) tma_reduce_add_2d(&tmap_out, slab, ns, m_base);
+                        else tma_store_2d(&tmap_out, slab, ns, m_base);
                         tma_commit_group();
                     }
                 }
             } else {
                 // direct row-per-thread stores (patch-embedding rows are re-mapped, 0.7 % of the step)
-                constexpr int kColsPerWarp = BLOCK_N / 2;
-                const int col0 = group * kColsPerWarp;
+                constexpr int kColsPerWarp = BLOCK_N / 4;
+                const int col0 = (group * 2 + sub) * kColsPerWarp;
                 const int row = m_base + row_in_tile;
                 const bool row_ok = row < p.M;
                 const int f = row / p.rows_in;
                 const long long out_row = (long long)f * p.rows_out + p.prefix + (row - f * p.rows_in);
 #pragma unroll 1
-                for (int c = 0; c < kColsPerWarp; c += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(taddr_row + col0 + c, v);
+                for (int c = 0; c < kColsPerWarp; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(taddr_row + col0 + c, v);
                     tmem_ld_wait();
                     const int n0 = n_blk * BLOCK_N + col0 + c;
                     if (row_ok) {
                         float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
+                        for (int j = 0; j < 16; j += 4) {
                             const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
                             *reinterpret_cast<float4*>(o + j) =
@@ -338,7 +335,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tc_fence_before();
     // pair: neither CTA may leave while the other can still touch its shared memory, barriers or TMEM
     if (CG == 2) cluster_sync_all(); else __syncthreads();
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         tc_fence_after();
         if (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }

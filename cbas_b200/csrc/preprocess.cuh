@@ -123,6 +123,95 @@ preprocess_resize_kernel(const uint8_t* __restrict__ frames, __nv_bfloat16* __re
     }
 }
 
+
+// Shared-memory version of the resize path for the common case (16-byte aligned rows): one CTA per (frame, patch
+// row).  The source rows the 16 output rows need are staged with 16-byte loads, resampled horizontally into an
+// fp32 strip, then vertically, normalised and written as 16-byte pieces of the patch matrix.  Every source byte
+// is read from HBM once (the per-pixel version above re-reads each one ~25 times through L1).
+struct ResizeTileGeom {
+    int max_rows;  // largest source-row span any patch row needs (host-computed from the taps)
+};
+
+__global__ void __launch_bounds__(256)
+preprocess_resize_tile_kernel(const uint8_t* __restrict__ frames, __nv_bfloat16* __restrict__ A, int H, int W,
+                              long long frame_stride, int row_stride, int S, ResizeTaps tp, float3 mean,
+                              float3 inv_std, int max_rows) {
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    const int ns = S >> 4;
+    const int f = blockIdx.x / ns, py = blockIdx.x % ns;
+    const int y_first = py * 16;
+    const int r0 = __ldg(tp.ymin + y_first);
+    int r1 = __ldg(tp.ymin + y_first + 15) + tp.taps_y;
+    r1 = r1 < H ? r1 : H;
+    const int nrows = r1 - r0;
+    const int row_bytes = W * 3;
+    const int src_pitch = (row_bytes + 15) & ~15;
+    uint8_t* src = rs_smem;                                                     // [max_rows][src_pitch]
+    float* hbuf = reinterpret_cast<float*>(rs_smem + max_rows * src_pitch);     // [max_rows][S*3]
+    const uint8_t* img = frames + f * frame_stride + (long long)r0 * row_stride;
+    // A: stage the source rows
+    const int vec_per_row = src_pitch >> 4;
+    for (int i = threadIdx.x; i < nrows * vec_per_row; i += blockDim.x) {
+        const int r = i / vec_per_row, v = i - r * vec_per_row;
+        const uint8_t* g = img + (long long)r * row_stride + v * 16;
+        uint4 q;
+        if (v * 16 + 16 <= row_bytes) q = __ldg(reinterpret_cast<const uint4*>(g));
+        else {
+            uint8_t tmp[16];
+#pragma unroll
+            for (int b = 0; b < 16; ++b) tmp[b] = (v * 16 + b < row_bytes) ? g[b] : 0;
+            q = *reinterpret_cast<uint4*>(tmp);
+        }
+        *reinterpret_cast<uint4*>(src + r * src_pitch + v * 16) = q;
+    }
+    __syncthreads();
+    // B: horizontal pass (fp32), all three channels of one (row, x) per thread iteration
+    for (int i = threadIdx.x; i < nrows * S; i += blockDim.x) {
+        const int r = i / S, x = i - r * S;
+        const int x0 = __ldg(tp.xmin + x);
+        const uint8_t* row = src + r * src_pitch;
+        float cr = 0.f, cg = 0.f, cb = 0.f;
+        for (int k = 0; k < tp.taps_x; ++k) {
+            const float w = __ldg(tp.wx + x * tp.taps_x + k);
+            const uint8_t* px = row + 3 * min(x0 + k, W - 1);
+            cr += w * float(px[0]);
+            cg += w * float(px[1]);
+            cb += w * float(px[2]);
+        }
+        float* o = hbuf + (r * S + x) * 3;
+        o[0] = cr; o[1] = cg; o[2] = cb;
+    }
+    __syncthreads();
+    // C: vertical pass, normalise, store 8 consecutive kx (16 bytes) per task
+    const float mu[3] = {mean.x, mean.y, mean.z}, is[3] = {inv_std.x, inv_std.y, inv_std.z};
+    const int tasks = 16 * (S >> 3) * 3;
+    for (int t = threadIdx.x; t < tasks; t += blockDim.x) {
+        const int c = t % 3;
+        const int gx = (t / 3) % (S >> 3);
+        const int ky = t / (3 * (S >> 3));
+        const int y = y_first + ky;
+        const int yr = __ldg(tp.ymin + y) - r0;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < tp.taps_y; ++j) {
+            const float w = __ldg(tp.wy + y * tp.taps_y + j);
+            const int r = min(yr + j, nrows - 1);
+            const float* hrow = hbuf + (r * S + gx * 8) * 3 + c;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += w * hrow[3 * i];
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            const float v0 = (acc[i] * (1.0f / 255.0f) - mu[c]) * is[c];
+            const float v1 = (acc[i + 1] * (1.0f / 255.0f) - mu[c]) * is[c];
+            o[i >> 1] = pack_bf16(v0, v1);
+        }
+        const int px = gx >> 1, kx0 = (gx & 1) * 8;
+        __nv_bfloat16* dst = A + ((long long)f * ns * ns + (long long)py * ns + px) * 768 + c * 256 + ky * 16 + kx0;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // CLS + register rows of the residual stream (HF modeling_dinov3_vit.py:86-90): h[frame*T + j] = prefix[j], j < P
 __global__ void __launch_bounds__(256)
 fill_prefix_kernel(float* __restrict__ h, const float* __restrict__ prefix_tokens, int n_frames, int T, int P, int D) {

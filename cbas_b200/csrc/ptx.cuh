@@ -345,20 +345,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// Same function through Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the bf16 rounding of the
-// result): one MUFU.RCP, one MUFU.EX2 and ~12 FMAs instead of erff's ~30 instructions, which keeps the
-// up-projection epilogue under the tile's MMA time.  1+erf(x) for x<0 is formed without cancellation.
+// Same function for the bf16-output GEMM epilogue, shaped for the FMA pipe (the up-projection epilogue is bound
+// by it): GELU(v) = max(v,0) - |v| * h(|v|),  h(a) = 0.5 erfc(a / sqrt 2) = 2^q(a), q a degree-6 fit of
+// log2(erfc) - 1 on [0, 6.22] with the 1/sqrt2 scale folded into the coefficients.  Six Horner FFMAs, one MUFU.EX2,
+// one closing FFMA and two FMNMX per element; max |error| 8.6e-6 (relative 6e-5) - far inside the bf16 rounding
+// (2e-3) of the stored result.  No cancellation for negative v.
 __device__ __forceinline__ float gelu_erf_fast(float v) {
-    const float x = v * 0.70710678118654752440f;
-    const float ax = fabsf(x);
-    const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float e = p * t * ex2_approx(-1.4426950408889634f * x * x);  // = 1 - erf(|x|)
-    const float half_e = 0.5f * e;
-    return v * (v >= 0.f ? 1.0f - half_e : half_e);
+    const float a = fminf(fabsf(v), 6.2225396744f);
+    float q = fmaf(2.161453813e-05f, a, -5.882218247e-04f);
+    q = fmaf(q, a, 7.054760586e-03f);
+    q = fmaf(q, a, -5.079342797e-02f);
+    q = fmaf(q, a, -4.617504478e-01f);
+    q = fmaf(q, a, -1.149972320e+00f);
+    q = fmaf(q, a, -1.000076532e+00f);
+    return fmaf(-fabsf(v), ex2_approx(q), fmaxf(v, 0.f));
 }
 
 }  // namespace cbas

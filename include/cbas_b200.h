@@ -97,6 +97,8 @@ int cbas_b200_encoder_debug_hidden(cbas_encoder* enc, const uint8_t* frames_dev,
  * 5 bias+GELU->f32 */
 int cbas_b200_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_dev, void* out_dev, int32_t M,
                         int32_t N, int32_t K, int32_t epi, void* stream);
+/* Test knob: 1 (default) = shared-memory tiled resize kernel when the geometry allows, 0 = per-pixel kernel. */
+int cbas_b200_debug_resize_tiled(int32_t on);
 /* Test knob: 0 = choose automatically (CTA pairs / tcgen05 cta_group::2 when M >= 4096), 1 or 2 = force. */
 int cbas_b200_debug_gemm_cta_group(int32_t cg);
 int cbas_b200_layernorm(const float* in_dev, const float* gamma_dev, const float* beta_dev, void* out_bf16_dev,
@@ -105,16 +107,12 @@ int cbas_b200_attention(const void* qkv_bf16_dev, void* out_bf16_dev, const floa
                         const float* rope_sin_dev, int32_t frames, int32_t T, int32_t prefix, int32_t heads,
                         void* stream);
 /* tcgen05 attention (frames of <= 256 tokens).  RoPE is applied in the kernel's prologue from the given tables
- * ([T - prefix, 32] f32); pass null tables when q and k arrive already rotated (cbas_b200_gemm_qkv_rope). */
+ * ([T - prefix, 32] f32); pass null tables to skip the rotation. */
 int cbas_b200_attention_tc(const void* qkv_bf16_dev, void* out_bf16_dev, const float* rope_cos_dev,
                            const float* rope_sin_dev, int32_t frames, int32_t T, int32_t prefix, int32_t heads,
                            void* stream);
-/* QKV projection with the RoPE epilogue: out_bf16 = rope(A W^T + bias) on columns [0, rope_cols) of patch tokens. */
-int cbas_b200_gemm_qkv_rope(const void* a_dev, const void* w_dev, const float* bias_dev, void* out_bf16_dev,
-                            int32_t M, int32_t N, int32_t K, const float* rope_cos_dev, const float* rope_sin_dev,
-                            int32_t T, int32_t prefix, int32_t rope_cols, void* stream);
-/* Test knob: 0 = automatic (tcgen05 when T <= 256), 1 = mma.sync kernel with RoPE prologue, 2 = tcgen05 with
- * RoPE prologue, 3 = tcgen05 with RoPE in the QKV GEMM epilogue. */
+/* Test knob: 0 = automatic (tcgen05 when T <= 256), 1 = mma.sync kernel, 2 = tcgen05 kernel (both rotate q and k
+ * in their prologue). */
 int cbas_b200_debug_attention_impl(int32_t impl);
 int cbas_b200_preprocess_green(const uint8_t* frames_dev, void* a_bf16_dev, int32_t n, int32_t H, int32_t W,
                                int64_t frame_stride, int32_t row_stride, void* stream);

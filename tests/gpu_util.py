@@ -56,13 +56,3 @@ def attention_tc(qkv_bf16, frames, T, heads, cos=None, sin=None, prefix=0):
                                                  sin.data_ptr() if sin is not None else None, frames, T, prefix, heads,
                                                  stream()), "attention_tc")
     return out
-
-
-def gemm_qkv_rope(a_bf16, w_bf16, bias, cos, sin, T, prefix, rope_cols):
-    M, K = a_bf16.shape
-    N = w_bf16.shape[0]
-    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    _lib.check(_lib.lib().cbas_b200_gemm_qkv_rope(a_bf16.data_ptr(), w_bf16.data_ptr(), bias.data_ptr(),
-                                                  out.data_ptr(), M, N, K, cos.data_ptr(), sin.data_ptr(), T, prefix,
-                                                  rope_cols, stream()), "gemm_qkv_rope")
-    return out

@@ -15,7 +15,7 @@ from oracle import encoder as oenc  # noqa: E402
 from tests.gpu_util import cosine_rows, rel_err  # noqa: E402
 
 
-@pytest.fixture(params=[2, 1, 3], ids=["attn_tcgen05", "attn_mma_sync", "attn_tcgen05_epilogue_rope"])
+@pytest.fixture(params=[2, 1], ids=["attn_tcgen05", "attn_mma_sync"])
 def attention_impl(request):
     """Both attention kernels: tcgen05 (RoPE in the QKV epilogue) and mma.sync (RoPE in its prologue)."""
     from cbas_b200 import _lib

@@ -51,7 +51,7 @@ def test_gemm_gelu_f32():
     a, w, b = _mk(1029, 256, 1152, seed=4)
     out = gemm(a, w, b, epi=5)
     want = torch.nn.functional.gelu(a.float() @ w.float().T + b)
-    assert rel_err(out, want) < 2e-5  # fast erf: |erf error| <= 1.5e-7
+    assert rel_err(out, want) < 3e-5  # epilogue GELU: |error| <= 8.6e-6 absolute (see gelu_erf_fast)
 
 
 def test_gemm_residual_inplace():

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 from cbas_b200 import _lib  # noqa: E402
 from cbas_b200.encoder import aa_bilinear_taps, rope_tables  # noqa: E402
 from oracle import encoder as oenc  # noqa: E402
-from tests.gpu_util import attention, attention_tc, gemm_qkv_rope, layernorm, rel_err, stream  # noqa: E402
+from tests.gpu_util import attention, attention_tc, layernorm, rel_err, stream  # noqa: E402
 
 
 @pytest.mark.parametrize("D", [384, 768, 1024])
@@ -84,21 +84,6 @@ def test_attention_tcgen05_rope_prologue(side, heads, frames):
     assert rel_err(out, legacy) < 1.5e-2
 
 
-def test_qkv_gemm_rope_epilogue():
-    n, heads, frames, P = 14, 6, 5, 5
-    T, D = n * n + P, heads * 64
-    cos, sin = rope_tables(n, n)
-    cos, sin = cos.cuda(), sin.cuda()
-    a = torch.randn(frames * T, D, device="cuda").to(torch.bfloat16)
-    w = (torch.randn(3 * D, D, device="cuda") * 0.05).to(torch.bfloat16)
-    b = torch.randn(3 * D, device="cuda")
-    out = gemm_qkv_rope(a, w, b, cos, sin, T, P, 2 * D).float()
-    y = (a.float() @ w.float().T + b).view(frames, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
-    q, k = _rope_ref(y[0], y[1], cos, sin)
-    want = torch.stack([q, k, y[2]]).permute(1, 3, 0, 2, 4).reshape(frames * T, 3 * D)
-    assert rel_err(out, want) < 6e-3
-
-
 def test_rope_tables_match_hf_module():
     from transformers import DINOv3ViTConfig
     from transformers.models.dinov3_vit.modeling_dinov3_vit import DINOv3ViTRopePositionEmbedding
@@ -121,8 +106,10 @@ def test_preprocess_green_exact():
     assert torch.equal(A.float().cpu(), want)  # bytes are exact in bf16
 
 
-@pytest.mark.parametrize("H,W,S", [(256, 256, 224), (96, 128, 64), (224, 224, 224), (48, 48, 64)])
-def test_preprocess_resize_matches_oracle(H, W, S):
+@pytest.mark.parametrize("tiled", [1, 0], ids=["tiled", "per_pixel"])
+@pytest.mark.parametrize("H,W,S", [(256, 256, 224), (96, 128, 64), (224, 224, 224), (48, 48, 64), (480, 640, 224)])
+def test_preprocess_resize_matches_oracle(H, W, S, tiled):
+    _lib.check(_lib.lib().cbas_b200_debug_resize_tiled(tiled), "knob")
     frames = oenc.synthetic_frames(2, H, W, seed=2)
     want = oenc.preprocess_processor(frames, S)  # [2,3,S,S]
     ns = S // 16
@@ -136,6 +123,7 @@ def test_preprocess_resize_matches_oracle(H, W, S):
     _lib.check(_lib.lib().cbas_b200_preprocess_resize(
         f.data_ptr(), A.data_ptr(), 2, H, W, H * W * 3, W * 3, S, ymin_d.data_ptr(), wy_d.data_ptr(), wy.shape[1],
         xmin_d.data_ptr(), wx_d.data_ptr(), wx.shape[1], stream()), "resize")
+    _lib.lib().cbas_b200_debug_resize_tiled(1)
     got = A.float().cpu()
     # <= 1 bf16 ulp: |x| <= 2.7 -> ulp 2^-7 at most
     err = (got - want).abs()
