@@ -3,9 +3,11 @@
 //
 //   TMA      : Q (two 128-row tiles), K and V ([TK,64] each) of the head straight out of the fused QKV
 //              activation into a double-buffered shared-memory set (SWIZZLE_128B), one item ahead.
-//   tcgen05  : S_mt = Q_mt K^T  (128 x TK x 64, fp32 in TMEM) for both query tiles;
-//              O_mt = P_mt V    (128 x 64 x TK) with P read FROM TMEM (bf16 written over S by the softmax
-//              warps) and V consumed MN-major exactly as TMA laid it down - no transposes, no P in smem.
+//   tcgen05  : S_mt = Q_mt K^T  (128 x TK x 64, bf16 operands, fp32 in TMEM) for both query tiles;
+//              O_mt = P_mt V    (128 x 64 x TK, f16 operands) with P read FROM TMEM (f16 pairs written over S
+//              by the softmax warps) and V consumed MN-major exactly as TMA laid it down - no transposes, no P
+//              in shared memory.  V arrives as IEEE f16 (the QKV GEMM stores that third of its output as f16,
+//              EPI_BIAS_BF16_VF16) so the probabilities can stay in the f16 the MUFU produces.
 //   softmax  : four warpgroups, two per query tile; a thread owns one query row and HALF of its keys (TMEM lane
 //              access is tied to warp_id % 4, so two warps share each lane quarter).  Pass 1 reads S for the
 //              partial row max (exchanged with the partner thread through shared memory), pass 2 re-reads S,
@@ -44,6 +46,7 @@ struct AttnTcParams {
     const float* rope_cos;     // [T - prefix, 32] fp32 or null (no RoPE in this kernel)
     const float* rope_sin;
     int prefix;
+    long long* trace;          // optional [items][16] clock64 stamps of CTA 0 (profiling aid; null in production)
 };
 
 __host__ __device__ inline int atc_set_bytes(int TK) { return 2 * 128 * 128 + 2 * TK * 128; }
@@ -77,6 +80,11 @@ __device__ __forceinline__ void atc_rope_unit(uint8_t* tile, int row, int c, con
     *plo = lo;
     *phi = hi;
 }
+
+#define ATC_STAMP(slot)                                                                       \
+    do {                                                                                      \
+        if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 16 + (slot)] = clock64();     \
+    } while (0)
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 128} over qkv [M, 3D]
@@ -153,13 +161,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
         if (lane == 0) {
             // ---------------------------------------------------------------- MMA issuer
             const uint32_t idesc_s = umma_idesc_bf16(128, TK);
-            const uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);
+            const uint32_t idesc_o = umma_idesc_f16_bmn(128, 64);
             int it = 0;
             for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
                 const int b = it & 1;
                 uint8_t* set = smem + b * set_bytes;
+                ATC_STAMP(0);
                 mbar_wait(rope ? &qk_ready[b] : &kv_full[b], (it >> 1) & 1);
                 tc_fence_after();
+                ATC_STAMP(1);
                 const uint64_t dk = umma_desc_sw128(smem_u32(set + 32768));
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
@@ -170,6 +180,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                     for (int k = 0; k < 4; ++k)
                         umma_bf16_ss(tmem_base + 256 * mt, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
                     umma_commit(&s_full[mt]);
+                    ATC_STAMP(2 + mt);
                 }
                 const uint64_t dv = umma_desc_sw128_mn(smem_u32(set + 32768 + TK * 128));
 #pragma unroll
@@ -185,6 +196,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                                      idesc_o, k != 0);
                     }
                     umma_commit(&o_full[mt]);
+                    ATC_STAMP(4 + mt);
                 }
                 umma_commit(&kv_empty[b]);  // every MMA that reads this shared-memory set has retired
             }
@@ -227,6 +239,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             const int f = w / p.heads, h = w % p.heads;
             mbar_wait(&s_full[mt], it & 1);
             tc_fence_after();
+            if (threadIdx.x == 0) ATC_STAMP(6);
             float sum = 0.f;
             // pass 1: partial row max over this thread's valid keys
             float mx = -INFINITY;
@@ -247,36 +260,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                 }
             }
             *my_max = mx;
+            if (threadIdx.x == 0) ATC_STAMP(7);
             named_bar_sync(1 + mt, 256);  // the two warpgroups of this query tile
+            if (threadIdx.x == 0) ATC_STAMP(8);
             if (warp_has_rows) {
                 mx = fmaxf(mx, *peer_max);
                 const float mc = mx * c;
-                // pass 2: p = exp2(s*c - max*c), partial row sum, bf16 pairs written over the consumed part of S
+                // pass 2: p = exp2(s*c - max*c) two at a time in half precision (ex2.approx.f16x2: the result IS the
+                // f16 tensor-core operand, no repacking), partial row sum, written over the consumed part of S
                 for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld_32x16(t_row + c0, v);
                     tmem_ld_wait();
                     uint32_t pk[8];
                     if (c0 + 16 <= T) {
-                        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), c, -mc));
-                            const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), c, -mc));
-                            s0 += e0;
-                            s1 += e1;
-                            pk[j >> 1] = pack_bf16(e0, e1);
-                        }
-                        sum += s0 + s1;
+                        for (int j = 0; j < 16; j += 2)
+                            pk[j >> 1] = ex2_approx_f16x2(pack_f16(fmaf(__uint_as_float(v[j]), c, -mc),
+                                                                   fmaf(__uint_as_float(v[j + 1]), c, -mc)));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; j += 2) {
-                            const float e0 = (c0 + j < T) ? ex2_approx(fmaf(__uint_as_float(v[j]), c, -mc)) : 0.f;
-                            const float e1 = (c0 + j + 1 < T) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), c, -mc)) : 0.f;
-                            sum += e0 + e1;
-                            pk[j >> 1] = pack_bf16(e0, e1);
+                            const float x0 = (c0 + j < T) ? fmaf(__uint_as_float(v[j]), c, -mc) : -INFINITY;
+                            const float x1 = (c0 + j + 1 < T) ? fmaf(__uint_as_float(v[j + 1]), c, -mc) : -INFINITY;
+                            pk[j >> 1] = ex2_approx_f16x2(pack_f16(x0, x1));
                         }
                     }
+                    // chunk sum: f16 pair tree (8 values <= 1 each), then fp32
+                    __half2 a0 = __hadd2(*reinterpret_cast<__half2*>(&pk[0]), *reinterpret_cast<__half2*>(&pk[1]));
+                    __half2 a1 = __hadd2(*reinterpret_cast<__half2*>(&pk[2]), *reinterpret_cast<__half2*>(&pk[3]));
+                    __half2 a2 = __hadd2(*reinterpret_cast<__half2*>(&pk[4]), *reinterpret_cast<__half2*>(&pk[5]));
+                    __half2 a3 = __hadd2(*reinterpret_cast<__half2*>(&pk[6]), *reinterpret_cast<__half2*>(&pk[7]));
+                    const float2 sf = __half22float2(__hadd2(__hadd2(a0, a1), __hadd2(a2, a3)));
+                    sum += sf.x + sf.y;
                     tmem_st_32x8(t_row + c_begin + ((c0 - c_begin) >> 1), pk);
                 }
                 tmem_st_wait();
@@ -285,12 +301,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[mt]);
+            if (threadIdx.x == 0) ATC_STAMP(9);
 
             // RoPE prologue of the NEXT item, hidden behind this item's PV MMAs
             if (rope && w + (int)gridDim.x < num_items) rotate_set((it + 1) & 1, it + 1);
 
+            if (threadIdx.x == 0) ATC_STAMP(10);
             mbar_wait(&o_full[mt], it & 1);
             tc_fence_after();
+            if (threadIdx.x == 0) ATC_STAMP(11);
             if (warp_has_rows) {
                 uint32_t v0[32];
                 tmem_ld_32x32(t_row + ATC_O_COL + 32 * half, v0);
@@ -302,6 +321,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&o_empty[mt]);
+                if (threadIdx.x == 0) ATC_STAMP(12);
                 if (row < T) {
                     __nv_bfloat16* o = p.out + ((long long)f * T + row) * p.D + h * 64 + 32 * half;
 #pragma unroll

@@ -78,6 +78,7 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* 
 }
 
 bool g_resize_tiled = true;  // false: per-pixel kernel (test knob)
+long long* g_attention_trace = nullptr;  // device buffer [64][16] for the stage-timing aid (tools/attn_trace.py)
 int g_attention_impl = 0;  // 0 auto (tcgen05 when T <= 256), 1 mma.sync, 2 tcgen05 (both rotate q,k in their prologue)
 
 bool attention_tc_fits(int T, int prefix) {
@@ -110,7 +111,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const floa
         configured_smem = smem;
     }
     AttnTcParams p{qkv, out, frames, heads, T, TK, D, 0.125f * 1.4426950408889634f, rope ? cs : nullptr,
-                   rope ? sn : nullptr, prefix};
+                   rope ? sn : nullptr, prefix, g_attention_trace};
     const int items = frames * heads;
     const int grid = items < sm_count() ? items : sm_count();
     attention_tc_kernel<<<grid, ATC_THREADS, smem, s>>>(tq, tkv, p);
@@ -221,8 +222,9 @@ int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
     GemmParams p{};
     p.M = M; p.N = 3 * D; p.K = D; p.bias = (const float*)L.b_qkv; p.out = e->qkv; p.ldo = 3 * D;
     if (use_attention_tc(e->T, c.prefix_tokens)) {
-        // plain QKV projection; the tcgen05 attention kernel rotates q and k in its prologue
-        if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16, s, PROF_QKV_GEMM))
+        // QKV projection (V stored as f16); the tcgen05 attention kernel rotates q and k in its prologue
+        p.f16_from = 2 * D;
+        if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16_VF16, s, PROF_QKV_GEMM))
             return rc;
         if (int rc = launch_attention_tc(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n,
                                          e->T, c.prefix_tokens, c.heads, s)) return rc;
@@ -350,6 +352,11 @@ int cbas_b200_attention_tc(const void* qkv_bf16_dev, void* out_bf16_dev, const f
                            void* stream) {
     return launch_attention_tc((const __nv_bfloat16*)qkv_bf16_dev, (__nv_bfloat16*)out_bf16_dev, rope_cos_dev,
                                rope_sin_dev, frames, T, prefix, heads, (cudaStream_t)stream);
+}
+
+int cbas_b200_debug_attention_trace(void* trace_dev) {
+    g_attention_trace = (long long*)trace_dev;
+    return 0;
 }
 
 int cbas_b200_debug_resize_tiled(int32_t on) {

@@ -97,6 +97,7 @@ int launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
         case EPI_PATCH_F32: return launch_one<BLOCK_N, EPI_PATCH_F32, CG>(ta, tb, p, stream);
         case EPI_BIAS_F32: return launch_one<BLOCK_N, EPI_BIAS_F32, CG>(ta, tb, p, stream);
         case EPI_BIAS_GELU_F32: return launch_one<BLOCK_N, EPI_BIAS_GELU_F32, CG>(ta, tb, p, stream);
+        case EPI_BIAS_BF16_VF16: return launch_one<BLOCK_N, EPI_BIAS_BF16_VF16, CG>(ta, tb, p, stream);
     }
     return fail("unknown GEMM epilogue " + std::to_string(epi));
 }

@@ -35,6 +35,7 @@ enum GemmEpilogue : int {
     EPI_PATCH_F32 = 3,       // resid_f32[row_map(m),n] = acc + bias[n]  (patch rows behind the prefix tokens)
     EPI_BIAS_F32 = 4,        // out_f32[m,n] = acc + bias[n]
     EPI_BIAS_GELU_F32 = 5,   // out_f32[m,n] = gelu_erf(acc + bias[n])
+    EPI_BIAS_BF16_VF16 = 6,  // EPI_BIAS_BF16, but columns >= f16_from are stored as IEEE f16 (the V third of QKV)
 };
 
 struct GemmParams {
@@ -44,6 +45,7 @@ struct GemmParams {
     int ldo;
     // EPI_PATCH_F32: A row m = frame*rows_in + p  ->  out row frame*rows_out + prefix + p
     int rows_in, rows_out, prefix;
+    int f16_from;  // EPI_BIAS_BF16_VF16: first column stored as f16 (multiple of 64)
 };
 
 constexpr int GEMM_BLOCK_M = 128;
@@ -53,7 +55,9 @@ constexpr int GEMM_EPI_WARPS = 16;
 constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_SLAB_BYTES = GEMM_BLOCK_M * 128;  // 128 rows x 128 B
 
-__host__ __device__ constexpr bool gemm_epi_out_bf16(int epi) { return epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16; }
+__host__ __device__ constexpr bool gemm_epi_out_bf16(int epi) {
+    return epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_BF16_VF16;
+}
 __host__ __device__ constexpr bool gemm_epi_staged(int epi) { return epi != EPI_PATCH_F32; }
 __host__ __device__ constexpr bool gemm_epi_double_stage(int epi) { return epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_GELU_F32; }
 __host__ __device__ constexpr int gemm_slab_cols(int epi) { return gemm_epi_out_bf16(epi) ? 64 : 32; }
@@ -274,10 +278,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     for (int j = 0; j < 4; ++j) {  // this thread's 4 of the row's 8 16-byte chunks, XOR-swizzled like TMA
                         uint4 q;
                         if constexpr (kOutBf16) {
-                            q.x = pack_bf16(x[8 * j + 0], x[8 * j + 1]);
-                            q.y = pack_bf16(x[8 * j + 2], x[8 * j + 3]);
-                            q.z = pack_bf16(x[8 * j + 4], x[8 * j + 5]);
-                            q.w = pack_bf16(x[8 * j + 6], x[8 * j + 7]);
+                            if (EPI == EPI_BIAS_BF16_VF16 && n0 >= p.f16_from) {
+                                q.x = pack_f16(x[8 * j + 0], x[8 * j + 1]);
+                                q.y = pack_f16(x[8 * j + 2], x[8 * j + 3]);
+                                q.z = pack_f16(x[8 * j + 4], x[8 * j + 5]);
+                                q.w = pack_f16(x[8 * j + 6], x[8 * j + 7]);
+                            } else {
+                                q.x = pack_bf16(x[8 * j + 0], x[8 * j + 1]);
+                                q.y = pack_bf16(x[8 * j + 2], x[8 * j + 3]);
+                                q.z = pack_bf16(x[8 * j + 4], x[8 * j + 5]);
+                                q.w = pack_bf16(x[8 * j + 6], x[8 * j + 7]);
+                            }
                         } else {
                             q.x = __float_as_uint(x[4 * j + 0]);
                             q.y = __float_as_uint(x[4 * j + 1]);

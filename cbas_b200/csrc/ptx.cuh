@@ -345,6 +345,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// two exp2 per MUFU issue, half precision in and out (the softmax numerators feed an f16 tensor-core operand anyway)
+__device__ __forceinline__ uint32_t ex2_approx_f16x2(uint32_t x) {
+    uint32_t y;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// kind::f16 instruction descriptor with f16 (not bf16) A and B, B MN-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16_bmn(uint32_t M, uint32_t N) {
+    return (1u << 4) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // Same function for the bf16-output GEMM epilogue, shaped for the FMA pipe (the up-projection epilogue is bound
 // by it): GELU(v) = max(v,0) - |v| * h(|v|),  h(a) = 0.5 erfc(a / sqrt 2) = 2^q(a), q a degree-6 fit of
 // log2(erfc) - 1 on [0, 6.22] with the 1/sqrt2 scale folded into the coefficients.  Six Horner FFMAs, one MUFU.EX2,

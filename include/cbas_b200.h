@@ -97,6 +97,9 @@ int cbas_b200_encoder_debug_hidden(cbas_encoder* enc, const uint8_t* frames_dev,
  * 5 bias+GELU->f32 */
 int cbas_b200_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_dev, void* out_dev, int32_t M,
                         int32_t N, int32_t K, int32_t epi, void* stream);
+/* Profiling aid: device buffer of 64*16 int64 that CTA 0 of the tcgen05 attention kernel fills with clock64()
+ * stamps per pipeline stage (null switches it off). */
+int cbas_b200_debug_attention_trace(void* trace_dev);
 /* Test knob: 1 (default) = shared-memory tiled resize kernel when the geometry allows, 0 = per-pixel kernel. */
 int cbas_b200_debug_resize_tiled(int32_t on);
 /* Test knob: 0 = choose automatically (CTA pairs / tcgen05 cta_group::2 when M >= 4096), 1 or 2 = force. */
@@ -106,7 +109,8 @@ int cbas_b200_layernorm(const float* in_dev, const float* gamma_dev, const float
 int cbas_b200_attention(const void* qkv_bf16_dev, void* out_bf16_dev, const float* rope_cos_dev,
                         const float* rope_sin_dev, int32_t frames, int32_t T, int32_t prefix, int32_t heads,
                         void* stream);
-/* tcgen05 attention (frames of <= 256 tokens).  RoPE is applied in the kernel's prologue from the given tables
+/* tcgen05 attention (frames of <= 256 tokens).  q and k are bf16, the V third of the buffer is IEEE f16 (that is how
+ * the encoder's QKV GEMM stores it for this kernel).  RoPE is applied in the kernel's prologue from the given tables
  * ([T - prefix, 32] f32); pass null tables to skip the rotation. */
 int cbas_b200_attention_tc(const void* qkv_bf16_dev, void* out_bf16_dev, const float* rope_cos_dev,
                            const float* rope_sin_dev, int32_t frames, int32_t T, int32_t prefix, int32_t heads,

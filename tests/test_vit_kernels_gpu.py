@@ -54,14 +54,24 @@ def test_attention_with_rope(side, heads, frames):
     assert e < 1.5e-2, f"attention rel err {e}"
 
 
+def _qkv_with_f16_v(frames, T, D, heads):
+    """QKV buffer as the encoder's GEMM lays it out for the tcgen05 kernel: q, k bf16; v IEEE f16 bits.
+    Returns the buffer and the exact values it encodes as [3, B, H, T, 64] fp32."""
+    raw = torch.randn(frames * T, 3 * D, device="cuda") * 1.5
+    qkv = raw.to(torch.bfloat16)
+    v16 = raw[:, 2 * D:].to(torch.float16)
+    qkv.view(torch.int16)[:, 2 * D:] = v16.view(torch.int16)
+    vals = torch.cat([qkv[:, :2 * D].float(), v16.float()], dim=1)
+    return qkv, vals.view(frames, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+
+
 @pytest.mark.parametrize("side,heads,frames", [(224, 12, 3), (224, 12, 40), (64, 6, 5), (160, 16, 7), (240, 12, 2)])
 def test_attention_tcgen05(side, heads, frames):
     """tcgen05 kernel (S and PV on the 5th-gen tensor cores, P in TMEM) vs torch SDPA; no RoPE inside."""
     n = side // 16
     T, D = n * n + 5, heads * 64
-    qkv = (torch.randn(frames * T, 3 * D, device="cuda") * 1.5).to(torch.bfloat16)
+    qkv, x = _qkv_with_f16_v(frames, T, D, heads)
     out = attention_tc(qkv, frames, T, heads).float()
-    x = qkv.float().view(frames, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
     want = F.scaled_dot_product_attention(x[0], x[1], x[2], scale=0.125).permute(0, 2, 1, 3).reshape(frames * T, D)
     e = rel_err(out, want)
     assert e < 1.5e-2, f"tcgen05 attention rel err {e}"
@@ -73,14 +83,14 @@ def test_attention_tcgen05_rope_prologue(side, heads, frames):
     T, P, D = n * n + 5, 5, heads * 64
     cos, sin = rope_tables(n, n)
     cos, sin = cos.cuda(), sin.cuda()
-    qkv = (torch.randn(frames * T, 3 * D, device="cuda") * 1.5).to(torch.bfloat16)
+    qkv, x = _qkv_with_f16_v(frames, T, D, heads)
     out = attention_tc(qkv, frames, T, heads, cos, sin, P).float()
-    x = qkv.float().view(frames, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
     q, k = _rope_ref(x[0], x[1], cos, sin)
     want = F.scaled_dot_product_attention(q, k, x[2], scale=0.125).permute(0, 2, 1, 3).reshape(frames * T, D)
     e = rel_err(out, want)
     assert e < 1.5e-2, f"tcgen05 attention + RoPE prologue rel err {e}"
-    legacy = attention(qkv, cos, sin, frames, T, P, heads).float()  # the mma.sync kernel does the same job
+    qkv_bf = torch.cat([qkv[:, :2 * D], x[2].permute(0, 2, 1, 3).reshape(frames * T, D).to(torch.bfloat16)], dim=1)
+    legacy = attention(qkv_bf.contiguous(), cos, sin, frames, T, P, heads).float()  # the mma.sync kernel, bf16 V
     assert rel_err(out, legacy) < 1.5e-2
 
 
