@@ -39,6 +39,16 @@ def flops_per_frame(D, L, I, side):
     return 2.0 * (Np * 768 * D + L * (4 * N * D * D + 2 * N * N * D + 2 * N * D * I))
 
 
+def flops_per_frame_executed(D, L, I, side):
+    """FLOPs actually issued: the last block projects K and V for every token but runs the query, attention, proj
+    and MLP for the CLS row only (the other rows of the final hidden state are never read, cbas.py:677)."""
+    Np = (side // 16) ** 2
+    N = Np + 5
+    layer = 2.0 * (4 * N * D * D + 2 * N * N * D + 2 * N * D * I)
+    last = 2.0 * (2 * N * D * D + 2 * D * D + 2 * N * D + 2 * D * I)
+    return flops_per_frame(D, L, I, side) - layer + last
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -357,7 +367,11 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": ach / peaks["hbm"] if ach else None, "traffic": None,
                     "share_of_step": prof[dom][0] / total_prof_ms}
-    forward = {"gflop_per_frame_dense": F / 1e9, "tflops": value / world * F / 1e12,
+    Fx = flops_per_frame_executed(a["hidden_size"], a["num_hidden_layers"], a["intermediate_size"], side)
+    forward = {"gflop_per_frame_dense": F / 1e9, "gflop_per_frame_executed": Fx / 1e9,
+               "note": "tflops / frac use the DENSE count (SURVEY 8d); executed is lower because the last block "
+                       "only computes what the pooled CLS row needs",
+               "tflops": value / world * F / 1e12, "tflops_executed": value / world * Fx / 1e12,
                "frac_of_bf16_peak": value / world * F / 1e12 / peaks["tf_sustained"], "kernels": breakdown}
 
     # ---- end to end through the public streaming API, frames in pinned host memory

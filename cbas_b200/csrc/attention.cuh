@@ -206,4 +206,115 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// CLS-query attention for the LAST block.  Only the CLS row of the final hidden state is ever read
+// (modeling_dinov3_vit.py:547-548 + cbas.py:677), so in the last block only the CLS query has to attend:
+// one warp per (frame, head) scores the CLS query against all T keys (RoPE applied to the patch-token keys on the
+// fly, fp32 math), soft-maxes over the warp and accumulates P V with the lanes striding the 64 output dims.
+// q_cls: [frames, D] bf16 (un-rotated: the CLS token is a prefix token); k and v live in the fused QKV buffer.
+__global__ void __launch_bounds__(128)
+cls_attention_kernel(const __nv_bfloat16* __restrict__ q_cls, const __nv_bfloat16* __restrict__ qkv,
+                     __nv_bfloat16* __restrict__ out, const float* __restrict__ rope_cos,
+                     const float* __restrict__ rope_sin, int frames, int T, int prefix, int heads, int D,
+                     float scale_log2, int v_is_f16) {
+    const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (item >= frames * heads) return;
+    const int frame = item / heads, head = item % heads;
+    const long long ld = 3ll * D;
+    const __nv_bfloat16* kbase = qkv + (long long)frame * T * ld + D + head * ATT_HEAD_DIM;
+    const __nv_bfloat16* vbase = kbase + D;
+    // every lane keeps the whole 64-d query (fp32)
+    float q[64];
+    {
+        const uint4* qp = reinterpret_cast<const uint4*>(q_cls + (long long)frame * D + head * ATT_HEAD_DIM);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint4 u = __ldg(qp + i);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16(w[j]);
+                q[8 * i + 2 * j] = f.x;
+                q[8 * i + 2 * j + 1] = f.y;
+            }
+        }
+    }
+    // scores: lane owns keys lane, lane+32, ...
+    constexpr int MAX_SLOTS = 9;  // T <= 288
+    float sc[MAX_SLOTS];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < MAX_SLOTS; ++s) {
+        const int t = s * 32 + lane;
+        float acc = -INFINITY;
+        if (t < T) {
+            const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long long)t * ld);
+            float k[64];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 u = __ldg(kp + i);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack_bf16(w[j]);
+                    k[8 * i + 2 * j] = f.x;
+                    k[8 * i + 2 * j + 1] = f.y;
+                }
+            }
+            acc = 0.f;
+            if (t >= prefix) {
+                const float4* cs = reinterpret_cast<const float4*>(rope_cos + (t - prefix) * 32);
+                const float4* sn = reinterpret_cast<const float4*>(rope_sin + (t - prefix) * 32);
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 c4 = __ldg(cs + i4), s4 = __ldg(sn + i4);
+                    const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = 4 * i4 + e;
+                        // the kernels that feed the tensor cores round the rotated key to bf16; do the same here
+                        const float klo = __bfloat162float(__float2bfloat16_rn(k[i] * cc[e] - k[i + 32] * ss[e]));
+                        const float khi = __bfloat162float(__float2bfloat16_rn(k[i + 32] * cc[e] + k[i] * ss[e]));
+                        acc = fmaf(q[i], klo, acc);
+                        acc = fmaf(q[i + 32], khi, acc);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) acc = fmaf(q[i], k[i], acc);
+            }
+            acc *= scale_log2;
+        }
+        sc[s] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int s = 0; s < MAX_SLOTS; ++s) {
+        sc[s] = (s * 32 + lane < T) ? exp2f(sc[s] - mx) : 0.f;
+        sum += sc[s];
+    }
+    sum = warp_sum(sum);
+    // O = P V: lane owns output dims 2*lane, 2*lane+1
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int s = 0; s < MAX_SLOTS; ++s) {
+        const int tmax = min(32, T - s * 32);
+        for (int j = 0; j < tmax; ++j) {
+            const float pj = __shfl_sync(0xffffffffu, sc[s], j);
+            const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(vbase + (long long)(s * 32 + j) * ld) + lane);
+            float2 v;
+            if (v_is_f16) v = __half22float2(*reinterpret_cast<const __half2*>(&raw));
+            else v = unpack_bf16(raw);
+            o0 = fmaf(pj, v.x, o0);
+            o1 = fmaf(pj, v.y, o1);
+        }
+    }
+    const float inv = 1.0f / sum;
+    reinterpret_cast<uint32_t*>(out + (long long)frame * D + head * ATT_HEAD_DIM)[lane] = pack_bf16(o0 * inv, o1 * inv);
+}
+
 }  // namespace cbas

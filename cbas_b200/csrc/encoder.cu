@@ -77,6 +77,7 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* 
     return check_cuda(cudaGetLastError(), "attention_kernel launch");
 }
 
+bool g_prune_last_layer = true;  // false: run the last block on every token (test knob)
 bool g_resize_tiled = true;  // false: per-pixel kernel (test knob)
 long long* g_attention_trace = nullptr;  // device buffer [64][16] for the stage-timing aid (tools/attn_trace.py)
 int g_attention_impl = 0;  // 0 auto (tcgen05 when T <= 256), 1 mma.sync, 2 tcgen05 (both rotate q,k in their prologue)
@@ -176,6 +177,9 @@ struct cbas_encoder {
     __nv_bfloat16* xn = nullptr;       // [max*T, D]   LN output / attention output
     __nv_bfloat16* qkv = nullptr;      // [max*T, 3D]
     __nv_bfloat16* u = nullptr;        // [max*T, I]
+    __nv_bfloat16* cls_q = nullptr;    // [max, D]  last block, CLS rows only: query
+    __nv_bfloat16* cls_att = nullptr;  // [max, D]  attention output
+    __nv_bfloat16* cls_xn = nullptr;   // [max, D]  LN2 output
 };
 
 namespace {
@@ -247,6 +251,50 @@ int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
     return launch_gemm(e->u, I, (const __nv_bfloat16*)L.w_down, I, p, EPI_RESID_F32, s, PROF_DOWN_GEMM);
 }
 
+// Last block, production path: the final hidden state is only read at the CLS row (HF :547-548, cbas.py:677), so
+// K and V are projected for every token but the query, attention output, proj, LN2 and the MLP run on the n CLS
+// rows alone.  Mathematically identical to the full block for the row that is kept.
+int encoder_last_layer_cls_only(cbas_encoder* e, int li, int n, cudaStream_t s) {
+    const cbas_encoder_cfg& c = e->cfg;
+    const cbas_layer_weights& L = e->layers[li];
+    const int D = c.hidden, I = c.intermediate, T = e->T, M = n * T;
+    const bool tc = use_attention_tc(T, c.prefix_tokens);
+    if (int rc = launch_layernorm<__nv_bfloat16>(e->h, 1, (const float*)L.ln1_g, (const float*)L.ln1_b, e->xn, M, D,
+                                                 c.ln_eps, s)) return rc;
+    const __nv_bfloat16* wqkv = (const __nv_bfloat16*)L.w_qkv;
+    const float* bqkv = (const float*)L.b_qkv;
+    GemmParams p{};
+    // K | V for all tokens -> columns [D, 3D) of the qkv buffer (V in the format the attention kernels expect)
+    p.M = M; p.N = 2 * D; p.K = D; p.bias = bqkv + D; p.out = e->qkv + D; p.ldo = 3 * D; p.f16_from = D;
+    if (int rc = launch_gemm(e->xn, D, wqkv + (size_t)D * D, D, p, tc ? EPI_BIAS_BF16_VF16 : EPI_BIAS_BF16, s,
+                             PROF_QKV_GEMM)) return rc;
+    // Q for the CLS rows only (A rows are T*D apart)
+    p = GemmParams{};
+    p.M = n; p.N = D; p.K = D; p.bias = bqkv; p.out = e->cls_q; p.ldo = D;
+    if (int rc = launch_gemm(e->xn, T * D, wqkv, D, p, EPI_BIAS_BF16, s, PROF_QKV_GEMM)) return rc;
+    {
+        ProfScope prof(PROF_ATTENTION, s);
+        const int items = n * c.heads;
+        cls_attention_kernel<<<(items * 32 + 127) / 128, 128, 0, s>>>(
+            e->cls_q, e->qkv, e->cls_att, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n, T,
+            c.prefix_tokens, c.heads, D, 0.125f * 1.4426950408889634f, tc ? 1 : 0);
+        count_launch();
+        if (int rc = check_cuda(cudaGetLastError(), "cls_attention_kernel launch")) return rc;
+    }
+    // proj + residual into the CLS rows of h (output rows are T*D apart)
+    p = GemmParams{};
+    p.M = n; p.N = D; p.K = D; p.bias = (const float*)L.b_o; p.out = e->h; p.ldo = T * D;
+    if (int rc = launch_gemm(e->cls_att, D, (const __nv_bfloat16*)L.w_o, D, p, EPI_RESID_F32, s, PROF_PROJ_GEMM)) return rc;
+    if (int rc = launch_layernorm<__nv_bfloat16>(e->h, T, (const float*)L.ln2_g, (const float*)L.ln2_b, e->cls_xn, n, D,
+                                                 c.ln_eps, s)) return rc;
+    p = GemmParams{};
+    p.M = n; p.N = I; p.K = D; p.bias = (const float*)L.b_up; p.out = e->u; p.ldo = I;
+    if (int rc = launch_gemm(e->cls_xn, D, (const __nv_bfloat16*)L.w_up, D, p, EPI_BIAS_GELU_BF16, s, PROF_UP_GEMM)) return rc;
+    p = GemmParams{};
+    p.M = n; p.N = D; p.K = I; p.bias = (const float*)L.b_down; p.out = e->h; p.ldo = T * D;
+    return launch_gemm(e->u, I, (const __nv_bfloat16*)L.w_down, I, p, EPI_RESID_F32, s, PROF_DOWN_GEMM);
+}
+
 int encoder_forward(cbas_encoder* e, const uint8_t* frames_u8, const float* planes, int n, long long fs, int rs,
                     int stop_after_layer, float* hidden_out, float* emb_out, cudaStream_t s) {
     if (!e) return fail("null encoder");
@@ -254,8 +302,13 @@ int encoder_forward(cbas_encoder* e, const uint8_t* frames_u8, const float* plan
     if (n == 0) return 0;
     if (int rc = encoder_embed(e, frames_u8, planes, n, fs, rs, s)) return rc;
     const int L = stop_after_layer >= 0 ? stop_after_layer : e->cfg.layers;
-    for (int li = 0; li < L; ++li)
-        if (int rc = encoder_layer(e, li, n, s)) return rc;
+    // only the pooled CLS embedding is wanted: the last block can skip every row that is thrown away
+    const bool prune = g_prune_last_layer && stop_after_layer < 0 && !hidden_out && e->T <= 288 && L >= 1;
+    for (int li = 0; li < L; ++li) {
+        if (prune && li == L - 1) {
+            if (int rc = encoder_last_layer_cls_only(e, li, n, s)) return rc;
+        } else if (int rc = encoder_layer(e, li, n, s)) return rc;
+    }
     const int D = e->cfg.hidden;
     if (hidden_out)
         CBAS_CHECK(cudaMemcpyAsync(hidden_out, e->h, (size_t)n * e->T * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -300,6 +353,9 @@ int cbas_b200_encoder_create(const cbas_encoder_cfg* cfg, const cbas_encoder_wei
     alloc((void**)&e->xn, mt * D * 2);
     alloc((void**)&e->qkv, mt * 3 * D * 2);
     alloc((void**)&e->u, mt * (size_t)cfg->intermediate * 2);
+    alloc((void**)&e->cls_q, (size_t)cfg->max_frames * D * 2);
+    alloc((void**)&e->cls_att, (size_t)cfg->max_frames * D * 2);
+    alloc((void**)&e->cls_xn, (size_t)cfg->max_frames * D * 2);
     if (err != cudaSuccess) {
         cbas_b200_encoder_destroy(e);
         return check_cuda(err, "encoder workspace cudaMalloc");
@@ -311,6 +367,7 @@ int cbas_b200_encoder_create(const cbas_encoder_cfg* cfg, const cbas_encoder_wei
 void cbas_b200_encoder_destroy(cbas_encoder* e) {
     if (!e) return;
     cudaFree(e->a_patch); cudaFree(e->h); cudaFree(e->xn); cudaFree(e->qkv); cudaFree(e->u);
+    cudaFree(e->cls_q); cudaFree(e->cls_att); cudaFree(e->cls_xn);
     delete e;
 }
 
@@ -356,6 +413,11 @@ int cbas_b200_attention_tc(const void* qkv_bf16_dev, void* out_bf16_dev, const f
 
 int cbas_b200_debug_attention_trace(void* trace_dev) {
     g_attention_trace = (long long*)trace_dev;
+    return 0;
+}
+
+int cbas_b200_debug_prune_last_layer(int32_t on) {
+    g_prune_last_layer = on != 0;
     return 0;
 }
 

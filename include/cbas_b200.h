@@ -100,6 +100,9 @@ int cbas_b200_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_
 /* Profiling aid: device buffer of 64*16 int64 that CTA 0 of the tcgen05 attention kernel fills with clock64()
  * stamps per pipeline stage (null switches it off). */
 int cbas_b200_debug_attention_trace(void* trace_dev);
+/* Test knob: 1 (default) = in the last block compute only what the pooled CLS row needs (K/V for all tokens, the
+ * rest for the CLS rows), 0 = run the last block on every token.  Same result for the row that is kept. */
+int cbas_b200_debug_prune_last_layer(int32_t on);
 /* Test knob: 1 (default) = shared-memory tiled resize kernel when the geometry allows, 0 = per-pixel kernel. */
 int cbas_b200_debug_resize_tiled(int32_t on);
 /* Test knob: 0 = choose automatically (CTA pairs / tcgen05 cta_group::2 when M >= 4096), 1 or 2 = force. */
