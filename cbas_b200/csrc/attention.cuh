@@ -209,112 +209,125 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 
 // ---------------------------------------------------------------------------------------------------------------
 // CLS-query attention for the LAST block.  Only the CLS row of the final hidden state is ever read
-// (modeling_dinov3_vit.py:547-548 + cbas.py:677), so in the last block only the CLS query has to attend:
-// one warp per (frame, head) scores the CLS query against all T keys (RoPE applied to the patch-token keys on the
-// fly, fp32 math), soft-maxes over the warp and accumulates P V with the lanes striding the 64 output dims.
+// (modeling_dinov3_vit.py:547-548 + cbas.py:677), so in the last block only the CLS query has to attend.
+// One warp per (frame, head); the warp walks the keys four at a time, EIGHT LANES PER KEY ROW (16 bytes each), so
+// every load instruction touches four full 128-byte lines instead of 32 different ones.  RoPE is applied to the
+// patch-token keys on the fly (the partner half of the row sits four lanes away), the rotated key is rounded to
+// bf16 exactly as the dense kernels do, scores go to a warp-private shared-memory row, then softmax and P V run
+// with the same lane layout and the four key groups are summed at the end.
 // q_cls: [frames, D] bf16 (un-rotated: the CLS token is a prefix token); k and v live in the fused QKV buffer.
+constexpr int CLS_ATT_MAX_T = 288;
 __global__ void __launch_bounds__(128)
 cls_attention_kernel(const __nv_bfloat16* __restrict__ q_cls, const __nv_bfloat16* __restrict__ qkv,
                      __nv_bfloat16* __restrict__ out, const float* __restrict__ rope_cos,
                      const float* __restrict__ rope_sin, int frames, int T, int prefix, int heads, int D,
                      float scale_log2, int v_is_f16) {
+    __shared__ float s_sc[4][CLS_ATT_MAX_T];
     const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (item >= frames * heads) return;
+    float* sc = s_sc[threadIdx.x >> 5];
     const int frame = item / heads, head = item % heads;
     const long long ld = 3ll * D;
     const __nv_bfloat16* kbase = qkv + (long long)frame * T * ld + D + head * ATT_HEAD_DIM;
     const __nv_bfloat16* vbase = kbase + D;
-    // every lane keeps the whole 64-d query (fp32)
-    float q[64];
+    const int g = lane >> 3, j = lane & 7;  // key group, 16-byte chunk of the row (elements 8j .. 8j+7)
+    float q[8];
     {
-        const uint4* qp = reinterpret_cast<const uint4*>(q_cls + (long long)frame * D + head * ATT_HEAD_DIM);
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(q_cls + (long long)frame * D + head * ATT_HEAD_DIM) + j);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint4 u = __ldg(qp + i);
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16(w[j]);
-                q[8 * i + 2 * j] = f.x;
-                q[8 * i + 2 * j + 1] = f.y;
-            }
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_bf16(w[e]);
+            q[2 * e] = f.x * scale_log2;
+            q[2 * e + 1] = f.y * scale_log2;
         }
     }
-    // scores: lane owns keys lane, lane+32, ...
-    constexpr int MAX_SLOTS = 9;  // T <= 288
-    float sc[MAX_SLOTS];
+    const float sgn = j < 4 ? -1.f : 1.f;  // rotate-half: lo' = lo c - hi s, hi' = hi c + lo s
+    const int iters = (T + 3) >> 2;
     float mx = -INFINITY;
-#pragma unroll
-    for (int s = 0; s < MAX_SLOTS; ++s) {
-        const int t = s * 32 + lane;
-        float acc = -INFINITY;
-        if (t < T) {
-            const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long long)t * ld);
-            float k[64];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint4 u = __ldg(kp + i);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = unpack_bf16(w[j]);
-                    k[8 * i + 2 * j] = f.x;
-                    k[8 * i + 2 * j + 1] = f.y;
-                }
-            }
-            acc = 0.f;
-            if (t >= prefix) {
-                const float4* cs = reinterpret_cast<const float4*>(rope_cos + (t - prefix) * 32);
-                const float4* sn = reinterpret_cast<const float4*>(rope_sin + (t - prefix) * 32);
-#pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {
-                    const float4 c4 = __ldg(cs + i4), s4 = __ldg(sn + i4);
-                    const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i = 4 * i4 + e;
-                        // the kernels that feed the tensor cores round the rotated key to bf16; do the same here
-                        const float klo = __bfloat162float(__float2bfloat16_rn(k[i] * cc[e] - k[i + 32] * ss[e]));
-                        const float khi = __bfloat162float(__float2bfloat16_rn(k[i + 32] * cc[e] + k[i] * ss[e]));
-                        acc = fmaf(q[i], klo, acc);
-                        acc = fmaf(q[i + 32], khi, acc);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 64; ++i) acc = fmaf(q[i], k[i], acc);
-            }
-            acc *= scale_log2;
+#pragma unroll 4
+    for (int it = 0; it < iters; ++it) {
+        const int t = 4 * it + g;
+        const bool live = t < T;
+        const bool rot = live && t >= prefix;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (live) u = __ldg(reinterpret_cast<const uint4*>(kbase + (long long)t * ld) + j);
+        float4 c0, c1, s0, s1;
+        if (rot) {
+            const float4* cs = reinterpret_cast<const float4*>(rope_cos + (t - prefix) * 32) + 2 * (j & 3);
+            const float4* sn = reinterpret_cast<const float4*>(rope_sin + (t - prefix) * 32) + 2 * (j & 3);
+            c0 = __ldg(cs); c1 = __ldg(cs + 1); s0 = __ldg(sn); s1 = __ldg(sn + 1);
+        } else {
+            c0 = c1 = make_float4(1.f, 1.f, 1.f, 1.f);
+            s0 = s1 = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        sc[s] = acc;
-        mx = fmaxf(mx, acc);
+        const uint32_t own[4] = {u.x, u.y, u.z, u.w};
+        uint32_t oth[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oth[e] = __shfl_xor_sync(0xffffffffu, own[e], 4);
+        const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        float acc = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 a = unpack_bf16(own[e]), b = unpack_bf16(oth[e]);
+            const float r0 = __bfloat162float(__float2bfloat16_rn(fmaf(sgn * b.x, ss[2 * e], a.x * cc[2 * e])));
+            const float r1 = __bfloat162float(__float2bfloat16_rn(fmaf(sgn * b.y, ss[2 * e + 1], a.y * cc[2 * e + 1])));
+            acc = fmaf(q[2 * e], r0, acc);
+            acc = fmaf(q[2 * e + 1], r1, acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (live) {
+            if (j == 0) sc[t] = acc;
+            mx = fmaxf(mx, acc);
+        }
     }
     mx = warp_max(mx);
+    __syncwarp();
     float sum = 0.f;
-#pragma unroll
-    for (int s = 0; s < MAX_SLOTS; ++s) {
-        sc[s] = (s * 32 + lane < T) ? exp2f(sc[s] - mx) : 0.f;
-        sum += sc[s];
+    for (int t = lane; t < T; t += 32) {
+        const float p = exp2f(sc[t] - mx);
+        sc[t] = p;
+        sum += p;
     }
     sum = warp_sum(sum);
-    // O = P V: lane owns output dims 2*lane, 2*lane+1
-    float o0 = 0.f, o1 = 0.f;
+    __syncwarp();
+    // O = P V, lane (g, j) accumulates dims 8j..8j+7 over the keys of its group
+    float o[8];
 #pragma unroll
-    for (int s = 0; s < MAX_SLOTS; ++s) {
-        const int tmax = min(32, T - s * 32);
-        for (int j = 0; j < tmax; ++j) {
-            const float pj = __shfl_sync(0xffffffffu, sc[s], j);
-            const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(vbase + (long long)(s * 32 + j) * ld) + lane);
-            float2 v;
-            if (v_is_f16) v = __half22float2(*reinterpret_cast<const __half2*>(&raw));
-            else v = unpack_bf16(raw);
-            o0 = fmaf(pj, v.x, o0);
-            o1 = fmaf(pj, v.y, o1);
+    for (int e = 0; e < 8; ++e) o[e] = 0.f;
+#pragma unroll 8
+    for (int it = 0; it < iters; ++it) {
+        const int t = 4 * it + g;
+        if (t < T) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(vbase + (long long)t * ld) + j);
+            const float p = sc[t];
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float2 v;
+                if (v_is_f16) v = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                else v = unpack_bf16(w[e]);
+                o[2 * e] = fmaf(p, v.x, o[2 * e]);
+                o[2 * e + 1] = fmaf(p, v.y, o[2 * e + 1]);
+            }
         }
     }
     const float inv = 1.0f / sum;
-    reinterpret_cast<uint32_t*>(out + (long long)frame * D + head * ATT_HEAD_DIM)[lane] = pack_bf16(o0 * inv, o1 * inv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+        o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+        o[e] *= inv;
+    }
+    if (g == 0) {
+        uint4 r;
+        r.x = pack_bf16(o[0], o[1]); r.y = pack_bf16(o[2], o[3]); r.z = pack_bf16(o[4], o[5]); r.w = pack_bf16(o[6], o[7]);
+        reinterpret_cast<uint4*>(out + (long long)frame * D + head * ATT_HEAD_DIM)[j] = r;
+    }
 }
 
 }  // namespace cbas
