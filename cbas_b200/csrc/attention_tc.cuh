@@ -15,13 +15,18 @@
 //   epilogue : each of the two threads of a row scales 32 of the 64 output columns by 1 / (sum_a + sum_b)
 //              -> bf16 -> [M, D] at column head*64.
 //
-//   RoPE     : attention prologue, in shared memory.  While the tensor core runs PV of item i, the softmax warps
-//              rotate the Q and K rows of item i+1 in place (rotate-half form, fp32 math, cos/sin held as
-//              half2 pairs in shared memory, built once per CTA from the fp32 tables), fence them to the
-//              async proxy and release the MMA warp through an mbarrier.  Rows of prefix tokens and rows past
-//              the frame are left alone.  (Pass null tables to skip RoPE, e.g. when the QKV epilogue did it.)
+//   RoPE     : attention prologue, in shared memory, by FOUR DEDICATED WARPS: as soon as Q and K of an item have
+//              landed they rotate the patch-token rows in place (rotate-half form, fp32 math, cos/sin held as
+//              half2 pairs in shared memory, built once per CTA from the fp32 tables), fence them to the async
+//              proxy and release the MMA warps through an mbarrier.  Q/K buffers are recycled as soon as the S
+//              MMAs that read them retire (V only after PV), so loads and rotation run a full item ahead of the
+//              tensor core.  Rows of prefix tokens and rows past the frame are left alone.  (Pass null tables to
+//              skip RoPE.)
+//   overlap  : each query tile has its OWN MMA-issuing warp and its own barrier chain
+//              (S -> softmax -> P V -> epilogue -> next S); tile 1 is started half an item late, so while one
+//              tile's warps are in the MUFU-bound softmax the other tile's MMAs, TMEM drain and global stores run.
 //
-// TMEM map (512 columns): query tile mt owns columns [256*mt, 256*mt+256): S at +0..TK; P (bf16 pairs) of the
+// TMEM map (512 columns): query tile mt owns columns [256*mt, 256*mt+256): S at +0..TK; P (f16 pairs) of the
 // first key half at +0..CA/2 and of the second half at +CA..+CA+(TK-CA)/2; O at +192..+256 (written only after
 // the softmax has consumed S, read back by the same warps).
 // Reference semantics: HF modeling_dinov3_vit.py:316-329 (SDPA, scale 1/8, no mask, non-causal).
@@ -31,10 +36,14 @@
 namespace cbas {
 
 // warps 0-7 softmax/epilogue of query tile 0 (0-3 first half of the keys, 4-7 second half), 8-15 of tile 1; then
-// (highest ids = highest issue priority) warp 16 TMA producer, 17 MMA issuer, 18 TMEM allocator, 19 idle
-constexpr int ATC_THREADS = 640;
+// warp 16 TMA producer (+ TMEM allocation), 17 / 18 MMA issuers of query tile 0 / 1, 19-22 RoPE rotation
+constexpr int ATC_THREADS = 736;
 constexpr int ATC_SOFTMAX_WARPS = 16;
-constexpr int ATC_PRODUCER_WARP = 16, ATC_MMA_WARP = 17, ATC_ALLOC_WARP = 18;
+constexpr int ATC_PRODUCER_WARP = 16, ATC_MMA_WARP0 = 17, ATC_ROT_WARP0 = 19, ATC_ROT_WARPS = 4;
+constexpr int ATC_TRACE_SLOTS = 24;
+#ifndef ATC_POLY_PAIRS
+#define ATC_POLY_PAIRS 2  // of the 8 probability pairs per 16 columns, how many are exponentiated on the FMA pipe
+#endif
 constexpr int ATC_XCHG_BYTES = 2 * 2 * 2 * 128 * 4;  // [max|sum][tile][half][row] floats
 constexpr int ATC_O_COL = 192;
 
@@ -46,13 +55,15 @@ struct AttnTcParams {
     const float* rope_cos;     // [T - prefix, 32] fp32 or null (no RoPE in this kernel)
     const float* rope_sin;
     int prefix;
-    long long* trace;          // optional [items][16] clock64 stamps of CTA 0 (profiling aid; null in production)
+    long long* trace;          // optional [64][ATC_TRACE_SLOTS] clock64 stamps of CTA 0 (profiling aid; null in production)
 };
 
 __host__ __device__ inline int atc_set_bytes(int TK) { return 2 * 128 * 128 + 2 * TK * 128; }
 __host__ __device__ inline int atc_rope_bytes(int T, int prefix) { return ((T - prefix) * 32 * 4 + 127) & ~127; }
+__host__ __device__ inline int atc_stage_bytes(int T) { return (T * 128 + 1023) & ~1023; }  // O rows, 128 B each
 __host__ __device__ inline int atc_smem_bytes(int TK, int T, int prefix, bool rope) {
-    return 2 * atc_set_bytes(TK) + (rope ? atc_rope_bytes(T, prefix) : 0) + ATC_XCHG_BYTES + 1024 + 256;
+    return 2 * atc_set_bytes(TK) + atc_stage_bytes(T) + (rope ? atc_rope_bytes(T, prefix) : 0) + ATC_XCHG_BYTES + 1024 +
+           256;
 }
 
 // Rotate the patch-token rows of one [rows,64] bf16 tile in place.  `u` enumerates (row, chunk pair): a warp
@@ -83,29 +94,34 @@ __device__ __forceinline__ void atc_rope_unit(uint8_t* tile, int row, int c, con
 
 #define ATC_STAMP(slot)                                                                       \
     do {                                                                                      \
-        if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 16 + (slot)] = clock64();     \
+        if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * ATC_TRACE_SLOTS + (slot)] = clock64();     \
     } while (0)
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 128} over qkv [M, 3D]
                     const __grid_constant__ CUtensorMap tmap_kv,  // box {64, TK}
+                    const __grid_constant__ CUtensorMap tmap_o,   // box {64, min(T,128), 1} over out [frames][T][D]
+                    const __grid_constant__ CUtensorMap tmap_o1,  // box {64, T-128, 1}: the rows of query tile 1
                     const AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int TK = p.TK, T = p.T;
     const int set_bytes = atc_set_bytes(TK);
     const bool rope = p.rope_cos != nullptr;
-    __half2* rope_tab = reinterpret_cast<__half2*>(smem + 2 * set_bytes);  // [T - prefix][32] (cos, sin)
-    float* xchg = reinterpret_cast<float*>(smem + 2 * set_bytes + (rope ? atc_rope_bytes(T, p.prefix) : 0));
+    uint8_t* ostage = smem + 2 * set_bytes;  // [T][128 B] output rows of the current item, swizzled per 128-row tile
+    __half2* rope_tab = reinterpret_cast<__half2*>(ostage + atc_stage_bytes(T));  // [T - prefix][32] (cos, sin)
+    float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(rope_tab) + (rope ? atc_rope_bytes(T, p.prefix) : 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + ATC_XCHG_BYTES);
-    uint64_t* kv_full = bars;        // [2] TMA -> (softmax warps, then) MMA
-    uint64_t* kv_empty = bars + 2;   // [2] MMA -> TMA
-    uint64_t* s_full = bars + 4;     // [2] per query tile: MMA -> softmax
-    uint64_t* p_full = bars + 6;     // [2] softmax -> MMA
-    uint64_t* o_full = bars + 8;     // [2] MMA -> epilogue
-    uint64_t* o_empty = bars + 10;   // [2] epilogue -> MMA (TMEM half free again)
-    uint64_t* qk_ready = bars + 12;  // [2] softmax warps -> MMA: Q and K of this set are rotated
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* qk_full = bars;        // [2] TMA -> rotation warps (or MMA when there is no RoPE): Q tiles + K landed
+    uint64_t* qk_empty = bars + 2;   // [2] both MMA warps -> TMA: the S MMAs that read this Q/K set retired
+    uint64_t* v_full = bars + 4;     // [2] TMA -> MMA
+    uint64_t* v_empty = bars + 6;    // [2] both MMA warps -> TMA: the PV MMAs retired
+    uint64_t* s_full = bars + 8;     // [2] per query tile: MMA -> softmax
+    uint64_t* p_full = bars + 10;    // [2] softmax -> MMA
+    uint64_t* o_full = bars + 12;    // [2] MMA -> epilogue
+    uint64_t* o_empty = bars + 14;   // [2] epilogue -> MMA (TMEM half free again)
+    uint64_t* qk_ready = bars + 16;  // [2] rotation warps -> MMA: Q and K of this set are rotated
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_items = p.frames * p.heads;
@@ -113,16 +129,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
     if (warp == ATC_PRODUCER_WARP && lane == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_kv);
+        tma_prefetch_desc(&tmap_o);
+        tma_prefetch_desc(&tmap_o1);
     }
-    if (warp == ATC_MMA_WARP && lane == 0) {
+    if (warp == ATC_MMA_WARP0 && lane == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1);
-            mbar_init(&kv_empty[i], 1);
+            mbar_init(&qk_full[i], 1);
+            mbar_init(&qk_empty[i], 2);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 2);
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 8);
             mbar_init(&o_full[i], 1);
             mbar_init(&o_empty[i], 8);
-            mbar_init(&qk_ready[i], ATC_SOFTMAX_WARPS);
+            mbar_init(&qk_ready[i], ATC_ROT_WARPS);
         }
         fence_mbar_init();
     }
@@ -131,7 +151,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
         for (int i = threadIdx.x; i < n; i += blockDim.x)
             rope_tab[i] = __floats2half2_rn(__ldg(p.rope_cos + i), __ldg(p.rope_sin + i));
     }
-    if (warp == ATC_ALLOC_WARP) {
+    if (warp == ATC_PRODUCER_WARP) {
         tmem_alloc(tmem_ptr_smem, 512);
         tmem_relinquish();
     }
@@ -148,60 +168,82 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                 const int b = it & 1;
                 const int f = w / p.heads, h = w % p.heads;
                 uint8_t* set = smem + b * set_bytes;
-                mbar_wait(&kv_empty[b], ((it >> 1) & 1) ^ 1);
-                mbar_arrive_expect_tx(&kv_full[b], set_bytes);
                 const int row0 = f * T;
-                tma_load_2d(set, &tmap_q, &kv_full[b], h * 64, row0);
-                tma_load_2d(set + 16384, &tmap_q, &kv_full[b], h * 64, row0 + 128);
-                tma_load_2d(set + 32768, &tmap_kv, &kv_full[b], p.D + h * 64, row0);
-                tma_load_2d(set + 32768 + TK * 128, &tmap_kv, &kv_full[b], 2 * p.D + h * 64, row0);
+                mbar_wait(&qk_empty[b], ((it >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&qk_full[b], 32768 + TK * 128);
+                tma_load_2d(set, &tmap_q, &qk_full[b], h * 64, row0);
+                tma_load_2d(set + 16384, &tmap_q, &qk_full[b], h * 64, row0 + 128);
+                tma_load_2d(set + 32768, &tmap_kv, &qk_full[b], p.D + h * 64, row0);
+                mbar_wait(&v_empty[b], ((it >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&v_full[b], TK * 128);
+                tma_load_2d(set + 32768 + TK * 128, &tmap_kv, &v_full[b], 2 * p.D + h * 64, row0);
             }
         }
-    } else if (warp == ATC_MMA_WARP) {
+    } else if (warp == ATC_MMA_WARP0 || warp == ATC_MMA_WARP0 + 1) {
         if (lane == 0) {
-            // ---------------------------------------------------------------- MMA issuer
+            // ---------------------------------------------------------------- MMA issuer of query tile mt
+            const int mt = warp - ATC_MMA_WARP0;
             const uint32_t idesc_s = umma_idesc_bf16(128, TK);
             const uint32_t idesc_o = umma_idesc_f16_bmn(128, 64);
+            const uint32_t t_tile = tmem_base + 256 * mt;
+            const int ka = (((TK >> 4) + 1) / 2);  // k-steps whose keys belong to the first half of the row
+            // start tile 1 half an item late: its MMAs / epilogue then fall into tile 0's softmax and vice versa
+            if (mt == 1) mbar_wait(&p_full[0], 0);
             int it = 0;
             for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
                 const int b = it & 1;
                 uint8_t* set = smem + b * set_bytes;
-                ATC_STAMP(0);
-                mbar_wait(rope ? &qk_ready[b] : &kv_full[b], (it >> 1) & 1);
+                ATC_STAMP(3 * mt);
+                mbar_wait(rope ? &qk_ready[b] : &qk_full[b], (it >> 1) & 1);
+                mbar_wait(&o_empty[mt], (it & 1) ^ 1);  // previous item's O (inside this S region) was drained
                 tc_fence_after();
-                ATC_STAMP(1);
                 const uint64_t dk = umma_desc_sw128(smem_u32(set + 32768));
+                const uint64_t dq = umma_desc_sw128(smem_u32(set + mt * 16384));
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    mbar_wait(&o_empty[mt], (it & 1) ^ 1);  // previous item's O (inside this S region) was drained
-                    tc_fence_after();
-                    const uint64_t dq = umma_desc_sw128(smem_u32(set + mt * 16384));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16_ss(tmem_base + 256 * mt, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-                    umma_commit(&s_full[mt]);
-                    ATC_STAMP(2 + mt);
-                }
+                for (int k = 0; k < 4; ++k) umma_bf16_ss(t_tile, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                umma_commit(&s_full[mt]);
+                umma_commit(&qk_empty[b]);
+                ATC_STAMP(3 * mt + 1);
                 const uint64_t dv = umma_desc_sw128_mn(smem_u32(set + 32768 + TK * 128));
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    mbar_wait(&p_full[mt], it & 1);
-                    tc_fence_after();
-                    const int ka = (((TK >> 4) + 1) / 2);  // k-steps whose keys belong to the first half of the row
-                    for (int k = 0; k < TK / 16; ++k) {    // 16 keys per MMA: 8 TMEM columns of P, 2048 B of V
-                        // P of keys [0,CA) sits at columns [0,CA/2); P of keys [CA,TK) at [CA, CA+(TK-CA)/2): each
-                        // softmax thread overwrites only columns of S that it has itself already consumed
-                        const int pcol = k < ka ? 8 * k : 16 * ka + 8 * (k - ka);
-                        umma_bf16_ts(tmem_base + 256 * mt + ATC_O_COL, tmem_base + 256 * mt + pcol, dv + 128 * k,
-                                     idesc_o, k != 0);
-                    }
-                    umma_commit(&o_full[mt]);
-                    ATC_STAMP(4 + mt);
+                mbar_wait(&v_full[b], (it >> 1) & 1);
+                mbar_wait(&p_full[mt], it & 1);
+                tc_fence_after();
+                for (int k = 0; k < TK / 16; ++k) {  // 16 keys per MMA: 8 TMEM columns of P, 2048 B of V
+                    // P of keys [0,CA) sits at columns [0,CA/2); P of keys [CA,TK) at [CA, CA+(TK-CA)/2): each
+                    // softmax thread overwrites only columns of S that it has itself already consumed
+                    const int pcol = k < ka ? 8 * k : 16 * ka + 8 * (k - ka);
+                    umma_bf16_ts(t_tile + ATC_O_COL, t_tile + pcol, dv + 128 * k, idesc_o, k != 0);
                 }
-                umma_commit(&kv_empty[b]);  // every MMA that reads this shared-memory set has retired
+                umma_commit(&o_full[mt]);
+                umma_commit(&v_empty[b]);
+                ATC_STAMP(3 * mt + 2);
             }
         }
-    } else if (warp < ATC_SOFTMAX_WARPS) {
+    } else if (warp >= ATC_ROT_WARP0) {
+        // ------------------------------------------------------------------- RoPE rotation warps
+        if (rope) {
+            const int rtid = threadIdx.x - ATC_ROT_WARP0 * 32;
+            const int nrot = T - p.prefix;     // rotated rows of Q, and again of K
+            const int units = 2 * nrot * 4;    // (row, chunk pair)
+            int it = 0;
+            for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
+                const int b = it & 1;
+                uint8_t* set = smem + b * set_bytes;
+                mbar_wait(&qk_full[b], (it >> 1) & 1);
+                if (rtid == 0) ATC_STAMP(16);
+                for (int u = rtid; u < units; u += ATC_ROT_WARPS * 32) {
+                    const int ridx = u >> 2, cpair = u & 3;
+                    const int isk = ridx >= nrot;
+                    const int tok = p.prefix + ridx - (isk ? nrot : 0);
+                    atc_rope_unit(isk ? set + 32768 : set, tok, cpair, rope_tab + (tok - p.prefix) * 32);
+                }
+                fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&qk_ready[b]);
+                if (rtid == 0) ATC_STAMP(17);
+            }
+        }
+    } else {
         // ------------------------------------------------------------------- softmax + epilogue warpgroups
         const int mt = warp >> 3;          // query tile
         const int half = (warp >> 2) & 1;  // which half of the keys (and of the output columns)
@@ -217,52 +259,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
         float* peer_max = xchg + ((0 * 2 + mt) * 2 + (half ^ 1)) * 128 + rit;
         float* my_sum = xchg + ((1 * 2 + mt) * 2 + half) * 128 + rit;
         float* peer_sum = xchg + ((1 * 2 + mt) * 2 + (half ^ 1)) * 128 + rit;
-        const int wtid = threadIdx.x;  // 0..511 over the softmax warps
-        // rotate Q (256 rows in two tiles) and K (TK rows) of the item that sits in buffer set `b`
-        auto rotate_set = [&](int b, int iter) {
-            mbar_wait(&kv_full[b], (iter >> 1) & 1);
-            uint8_t* set = smem + b * set_bytes;
-            const int units = (256 + TK) * 4;
-            for (int u = wtid; u < units; u += ATC_SOFTMAX_WARPS * 32) {
-                const int r = u >> 2, cpair = u & 3;
-                const int tok = r < 256 ? r : r - 256;
-                if (tok >= p.prefix && tok < T)
-                    atc_rope_unit(r < 256 ? set : set + 32768 - 256 * 128, r, cpair, rope_tab + (tok - p.prefix) * 32);
-            }
-            fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&qk_ready[b]);
-        };
-        if (rope && (int)blockIdx.x < num_items) rotate_set(0, 0);
+        const bool stamper = (threadIdx.x & 255) == 0;  // first thread of each query tile
+        const int sbase = 6 + 5 * mt;
         int it = 0;
         for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
             const int f = w / p.heads, h = w % p.heads;
             mbar_wait(&s_full[mt], it & 1);
             tc_fence_after();
-            if (threadIdx.x == 0) ATC_STAMP(6);
+            if (stamper) ATC_STAMP(sbase);
             float sum = 0.f;
             // pass 1: partial row max over this thread's valid keys
             float mx = -INFINITY;
             if (warp_has_rows) {
-                for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld_32x16(t_row + c0, v);
+                int c0 = c_begin;
+                for (; c0 + 32 <= c_end; c0 += 32) {  // 32 columns per TMEM round trip
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + c0, v);
                     tmem_ld_wait();
-                    if (c0 + 16 <= T) {
+                    if (c0 + 32 <= T) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 2)
+                        for (int j = 0; j < 32; j += 2)
                             mx = fmaxf(mx, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
+                        for (int j = 0; j < 32; ++j)
                             if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
                     }
                 }
+                if (c0 < c_end) {  // 16-column tail (c_end - c_begin is a multiple of 16)
+                    uint32_t v[16];
+                    tmem_ld_32x16(t_row + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
+                }
             }
             *my_max = mx;
-            if (threadIdx.x == 0) ATC_STAMP(7);
             named_bar_sync(1 + mt, 256);  // the two warpgroups of this query tile
-            if (threadIdx.x == 0) ATC_STAMP(8);
+            if (stamper) ATC_STAMP(sbase + 1);
             if (warp_has_rows) {
                 mx = fmaxf(mx, *peer_max);
                 const float mc = mx * c;
@@ -275,9 +310,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                     uint32_t pk[8];
                     if (c0 + 16 <= T) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 2)
-                            pk[j >> 1] = ex2_approx_f16x2(pack_f16(fmaf(__uint_as_float(v[j]), c, -mc),
-                                                                   fmaf(__uint_as_float(v[j + 1]), c, -mc)));
+                        for (int j = 0; j < 16; j += 2) {
+                            const float x0 = fmaf(__uint_as_float(v[j]), c, -mc);
+                            const float x1 = fmaf(__uint_as_float(v[j + 1]), c, -mc);
+                            // the MUFU (16 ex2/clk/SM) is the busiest unit of this kernel: the last ATC_POLY_PAIRS
+                            // pairs of every 16 go through the FMA-pipe polynomial instead
+                            if ((j >> 1) < 8 - ATC_POLY_PAIRS) pk[j >> 1] = ex2_approx_f16x2(pack_f16(x0, x1));
+                            else pk[j >> 1] = pack_f16(ex2_poly3(x0), ex2_poly3(x1));
+                        }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; j += 2) {
@@ -301,15 +341,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[mt]);
-            if (threadIdx.x == 0) ATC_STAMP(9);
+            if (stamper) ATC_STAMP(sbase + 2);
 
-            // RoPE prologue of the NEXT item, hidden behind this item's PV MMAs
-            if (rope && w + (int)gridDim.x < num_items) rotate_set((it + 1) & 1, it + 1);
-
-            if (threadIdx.x == 0) ATC_STAMP(10);
             mbar_wait(&o_full[mt], it & 1);
             tc_fence_after();
-            if (threadIdx.x == 0) ATC_STAMP(11);
+            if (stamper) ATC_STAMP(sbase + 3);
             if (warp_has_rows) {
                 uint32_t v0[32];
                 tmem_ld_32x32(t_row + ATC_O_COL + 32 * half, v0);
@@ -317,35 +353,43 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                 // read the partner's partial sum BEFORE releasing the tile: once o_empty completes the partner may
                 // run ahead into the next item and overwrite it
                 const float inv_sum = 1.0f / (sum + *peer_sum);
-                // O is in registers: hand the TMEM half back before the global stores
+                // O is in registers: hand the TMEM half back before the stores
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&o_empty[mt]);
-                if (threadIdx.x == 0) ATC_STAMP(12);
-                if (row < T) {
-                    __nv_bfloat16* o = p.out + ((long long)f * T + row) * p.D + h * 64 + 32 * half;
+                // stage this thread's 64 bytes, 128-byte swizzled like TMA wants it
+                uint8_t* srow = ostage + row * 128;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 q;
-                        q.x = pack_bf16(__uint_as_float(v0[j]) * inv_sum, __uint_as_float(v0[j + 1]) * inv_sum);
-                        q.y = pack_bf16(__uint_as_float(v0[j + 2]) * inv_sum, __uint_as_float(v0[j + 3]) * inv_sum);
-                        q.z = pack_bf16(__uint_as_float(v0[j + 4]) * inv_sum, __uint_as_float(v0[j + 5]) * inv_sum);
-                        q.w = pack_bf16(__uint_as_float(v0[j + 6]) * inv_sum, __uint_as_float(v0[j + 7]) * inv_sum);
-                        *reinterpret_cast<uint4*>(o + j) = q;
-                    }
+                for (int j = 0; j < 32; j += 8) {
+                    uint4 q;
+                    q.x = pack_bf16(__uint_as_float(v0[j]) * inv_sum, __uint_as_float(v0[j + 1]) * inv_sum);
+                    q.y = pack_bf16(__uint_as_float(v0[j + 2]) * inv_sum, __uint_as_float(v0[j + 3]) * inv_sum);
+                    q.z = pack_bf16(__uint_as_float(v0[j + 4]) * inv_sum, __uint_as_float(v0[j + 5]) * inv_sum);
+                    q.w = pack_bf16(__uint_as_float(v0[j + 6]) * inv_sum, __uint_as_float(v0[j + 7]) * inv_sum);
+                    if (row < T) *reinterpret_cast<uint4*>(srow + (((half * 4 + (j >> 3)) ^ (rit & 7)) << 4)) = q;
                 }
             } else {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&o_empty[mt]);
             }
+            // one coalesced TMA store per query tile.  The staging rows are rewritten only in the next item's epilogue,
+            // which this thread's tile reaches through the max-exchange barrier, i.e. after the wait below.
+            fence_proxy_async();
+            named_bar_sync(3 + mt, 256);
+            if (stamper && mt * 128 < T) {
+                tma_store_3d(mt ? &tmap_o1 : &tmap_o, ostage + mt * 16384, h * 64, mt * 128, f);
+                tma_commit_group();
+                tma_wait_group_read<0>();
+            }
+            if (stamper) ATC_STAMP(sbase + 4);
         }
     }
 
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == ATC_ALLOC_WARP) {
+    if (warp == ATC_PRODUCER_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }

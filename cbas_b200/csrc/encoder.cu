@@ -79,7 +79,7 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* 
 
 bool g_prune_last_layer = true;  // false: run the last block on every token (test knob)
 bool g_resize_tiled = true;  // false: per-pixel kernel (test knob)
-long long* g_attention_trace = nullptr;  // device buffer [64][16] for the stage-timing aid (tools/attn_trace.py)
+long long* g_attention_trace = nullptr;  // device buffer [64][ATC_TRACE_SLOTS] for the stage-timing aid (tools/attn_trace.py)
 int g_attention_impl = 0;  // 0 auto (tcgen05 when T <= 256), 1 mma.sync, 2 tcgen05 (both rotate q,k in their prologue)
 
 bool attention_tc_fits(int T, int prefix) {
@@ -99,9 +99,14 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const floa
     ProfScope prof(PROF_ATTENTION, s);
     const int D = heads * 64;
     const long long M = (long long)frames * T;
-    CUtensorMap tq, tkv;
+    CUtensorMap tq, tkv, to, to1;
     if (int rc = make_tmap_2d(&tq, qkv, false, (int)M, 3 * D, 3 * D, 64, 128)) return rc;
     if (int rc = make_tmap_2d(&tkv, qkv, false, (int)M, 3 * D, 3 * D, 64, TK)) return rc;
+    // the output as [frames][T][D]: a 128-row store box is clipped at the end of ITS frame
+    if (int rc = make_tmap_3d_bf16(&to, out, D, T, frames, D, 64, T < 128 ? T : 128)) return rc;
+    to1 = to;
+    if (T > 128)
+        if (int rc = make_tmap_3d_bf16(&to1, out, D, T, frames, D, 64, T - 128)) return rc;
     const bool rope = cs != nullptr && sn != nullptr;
     if (rope && (prefix < 0 || prefix >= T)) return fail("attention: bad prefix token count");
     const int smem = atc_smem_bytes(TK, T, prefix, rope);
@@ -115,7 +120,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const floa
                    rope ? sn : nullptr, prefix, g_attention_trace};
     const int items = frames * heads;
     const int grid = items < sm_count() ? items : sm_count();
-    attention_tc_kernel<<<grid, ATC_THREADS, smem, s>>>(tq, tkv, p);
+    attention_tc_kernel<<<grid, ATC_THREADS, smem, s>>>(tq, tkv, to, to1, p);
     count_launch();
     return check_cuda(cudaGetLastError(), "attention_tc_kernel launch");
 }

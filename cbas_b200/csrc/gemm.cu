@@ -132,4 +132,19 @@ int make_tmap_2d(CUtensorMap* map, const void* base, bool f32, int rows, int col
     return make_tmap(map, base, f32, rows, cols, ld, box_cols, box_rows);
 }
 
+// bf16 [d2][d1][d0] tensor (d0 contiguous, row pitch ld elements, slab pitch d1*ld), box box0 x box1 x 1, SWIZZLE_128B
+int make_tmap_3d_bf16(CUtensorMap* map, const void* base, int d0, int d1, int d2, int ld, int box0, int box1) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)d1};
+    cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (3-D) failed with CUresult " + std::to_string((int)r));
+    return 0;
+}
+
 }  // namespace cbas

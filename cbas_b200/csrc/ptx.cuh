@@ -86,6 +86,13 @@ __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_
                  "r"(smem_u32(smem_src)), "r"(crd_inner), "r"(crd_outer)
                  : "memory");
 }
+// 3-D tiled store (coordinates innermost first); rows past a dimension's extent are clipped by the hardware
+__device__ __forceinline__ void tma_store_3d(const void* desc, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(desc)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* smem_src, int crd_inner,
                                                   int crd_outer) {
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -346,6 +353,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 // two exp2 per MUFU issue, half precision in and out (the softmax numerators feed an f16 tensor-core operand anyway)
+// 2^x on the FMA pipe for x <= 0 (softmax numerators): round-to-nearest split x = n + f with the 1.5*2^23 trick,
+// degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max rel err 7.5e-5, far below f16/bf16 rounding), then n is
+// added straight into the exponent field.  Inputs below -30 return 2^-30 (rounds to 0 as an f16 probability).
+// Lets a kernel whose MUFU is saturated (16 ex2/clk/SM) run part of its exponentials on the 128-lane FMA pipe.
+__device__ __forceinline__ float ex2_poly3(float x) {
+    x = fmaxf(x, -30.f);
+    const float t = x + 12582912.f;
+    const float f = x - (t - 12582912.f);
+    float p = fmaf(f, 0.05517089366912842f, 0.24261131882667542f);
+    p = fmaf(p, f, 0.6932610273361206f);
+    p = fmaf(p, f, 0.9999280571937561f);
+    return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
 __device__ __forceinline__ uint32_t ex2_approx_f16x2(uint32_t x) {
     uint32_t y;
     asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));

@@ -9,13 +9,15 @@ frames, heads, T = 512, 12, 201
 cos, sin = rope_tables(14, 14); cos, sin = cos.cuda(), sin.cuda()
 qkv = (torch.randn(frames * T, 3 * heads * 64, device="cuda")).to(torch.bfloat16)
 for _ in range(3): attention_tc(qkv, frames, T, heads, cos, sin, 5)
-tr = torch.zeros(64 * 16, dtype=torch.int64, device="cuda")
+S = 24
+tr = torch.zeros(64 * S, dtype=torch.int64, device="cuda")
 _lib.lib().cbas_b200_debug_attention_trace(tr.data_ptr())
 attention_tc(qkv, frames, T, heads, cos, sin, 5); torch.cuda.synchronize()
 _lib.lib().cbas_b200_debug_attention_trace(None)
-t = tr.cpu().numpy().reshape(64, 16)
-names = ["mma:loop_top", "mma:qk_ready", "mma:S0_issued", "mma:S1_issued", "mma:PV0_issued", "mma:PV1_issued",
-         "sm:s_full", "sm:pass1_done", "sm:max_xchg", "sm:p_full_arrived", "sm:rotate_done", "sm:o_full", "sm:o_empty_arrived"]
-base = t[4, 0]
+t = tr.cpu().numpy().reshape(64, S)
+names = {0: "mma0:top", 1: "mma0:S", 2: "mma0:PV", 3: "mma1:top", 4: "mma1:S", 5: "mma1:PV",
+         6: "sm0:s_full", 7: "sm0:max", 8: "sm0:p_full", 9: "sm0:o_full", 10: "sm0:done",
+         11: "sm1:s_full", 12: "sm1:max", 13: "sm1:p_full", 14: "sm1:o_full", 15: "sm1:done",
+         16: "rot:start", 17: "rot:done"}
 for it in range(4, 12):
-    print("item", it, " ".join(f"{n.split(':')[1]}={t[it, i] - t[it, 0]}" for i, n in enumerate(names)), " | item period", t[it + 1, 0] - t[it, 0])
+    print("item", it, " ".join(f"{n}={t[it, i] - t[it, 0]}" for i, n in names.items()), " | item period", t[it + 1, 0] - t[it, 0])
