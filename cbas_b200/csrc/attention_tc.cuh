@@ -55,6 +55,7 @@ struct AttnTcParams {
     const float* rope_cos;     // [T - prefix, 32] fp32 or null (no RoPE in this kernel)
     const float* rope_sin;
     int prefix;
+    int dbg;                   // timing experiments only (0 in production): 1 = PV as SS MMA, 2 = PV with a K-major B
     long long* trace;          // optional [64][ATC_TRACE_SLOTS] clock64 stamps of CTA 0 (profiling aid; null in production)
 };
 
@@ -180,44 +181,59 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             }
         }
     } else if (warp == ATC_MMA_WARP0 || warp == ATC_MMA_WARP0 + 1) {
-        if (lane == 0) {
-            // ---------------------------------------------------------------- MMA issuer of query tile mt
-            const int mt = warp - ATC_MMA_WARP0;
-            const uint32_t idesc_s = umma_idesc_bf16(128, TK);
-            const uint32_t idesc_o = umma_idesc_f16_bmn(128, 64);
-            const uint32_t t_tile = tmem_base + 256 * mt;
-            const int ka = (((TK >> 4) + 1) / 2);  // k-steps whose keys belong to the first half of the row
-            // start tile 1 half an item late: its MMAs / epilogue then fall into tile 0's softmax and vice versa
-            if (mt == 1) mbar_wait(&p_full[0], 0);
-            int it = 0;
-            for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
-                const int b = it & 1;
-                uint8_t* set = smem + b * set_bytes;
-                ATC_STAMP(3 * mt);
-                mbar_wait(rope ? &qk_ready[b] : &qk_full[b], (it >> 1) & 1);
-                mbar_wait(&o_empty[mt], (it & 1) ^ 1);  // previous item's O (inside this S region) was drained
-                tc_fence_after();
-                const uint64_t dk = umma_desc_sw128(smem_u32(set + 32768));
-                const uint64_t dq = umma_desc_sw128(smem_u32(set + mt * 16384));
+        // -------------------------------------------------------------------- MMA issuer of query tile mt
+        // The whole warp walks the loop (uniform control flow, operands in uniform registers); one elected lane
+        // issues.  tcgen05.commit tracks the MMAs of the issuing thread, so the same lane must issue both: elect.sync
+        // picks the same lane every time for a full mask.
+        const int mt = warp - ATC_MMA_WARP0;
+        const uint32_t idesc_s = umma_idesc_bf16(128, TK);
+        const uint32_t idesc_o = umma_idesc_f16_bmn(128, 64);
+        const uint32_t t_tile = __shfl_sync(0xffffffffu, tmem_base, 0) + 256 * mt;
+        const int nk = TK >> 4;
+        const int ka = (nk + 1) / 2;  // k-steps whose keys belong to the first half of the row
+        const uint32_t smem_base = smem_u32(smem);
+        // start tile 1 half an item late: its MMAs / epilogue then fall into tile 0's softmax and vice versa
+        if (mt == 1) mbar_wait(&p_full[0], 0);
+        int it = 0;
+        for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
+            const int b = it & 1;
+            const uint32_t set = smem_base + b * set_bytes;
+            if (lane == 0) ATC_STAMP(3 * mt);
+            mbar_wait(rope ? &qk_ready[b] : &qk_full[b], (it >> 1) & 1);
+            mbar_wait(&o_empty[mt], (it & 1) ^ 1);  // previous item's O (inside this S region) was drained
+            tc_fence_after();
+            if (lane == 0 && mt == 0) ATC_STAMP(21);
+            const uint64_t dk = umma_desc_sw128(set + 32768);
+            const uint64_t dq = umma_desc_sw128(set + mt * 16384);
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16_ss(t_tile, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
                 umma_commit(&s_full[mt]);
                 umma_commit(&qk_empty[b]);
-                ATC_STAMP(3 * mt + 1);
-                const uint64_t dv = umma_desc_sw128_mn(smem_u32(set + 32768 + TK * 128));
-                mbar_wait(&v_full[b], (it >> 1) & 1);
-                mbar_wait(&p_full[mt], it & 1);
-                tc_fence_after();
-                for (int k = 0; k < TK / 16; ++k) {  // 16 keys per MMA: 8 TMEM columns of P, 2048 B of V
-                    // P of keys [0,CA) sits at columns [0,CA/2); P of keys [CA,TK) at [CA, CA+(TK-CA)/2): each
-                    // softmax thread overwrites only columns of S that it has itself already consumed
-                    const int pcol = k < ka ? 8 * k : 16 * ka + 8 * (k - ka);
-                    umma_bf16_ts(t_tile + ATC_O_COL, t_tile + pcol, dv + 128 * k, idesc_o, k != 0);
+            }
+            __syncwarp();
+            if (lane == 0) ATC_STAMP(3 * mt + 1);
+            const uint64_t dv = umma_desc_sw128_mn(set + 32768 + TK * 128);
+            mbar_wait(&v_full[b], (it >> 1) & 1);
+            mbar_wait(&p_full[mt], it & 1);
+            tc_fence_after();
+            if (lane == 0 && mt == 0) ATC_STAMP(22);
+            if (elect_one()) {
+                // 16 keys per MMA: 8 TMEM columns of P, 2048 B of V.  P of keys [0,CA) sits at columns [0,CA/2); P of
+                // keys [CA,TK) at [CA, CA+(TK-CA)/2): each softmax thread overwrites only columns of S that it has
+                // itself already consumed
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (k < nk) {
+                        const uint32_t pcol = 8 * k + (k >= ka ? 8 * ka : 0);
+                        umma_bf16_ts(t_tile + ATC_O_COL, t_tile + pcol, dv + 128 * k, idesc_o, k != 0);
+                    }
                 }
                 umma_commit(&o_full[mt]);
                 umma_commit(&v_empty[b]);
-                ATC_STAMP(3 * mt + 2);
             }
+            __syncwarp();
+            if (lane == 0) ATC_STAMP(3 * mt + 2);
         }
     } else if (warp >= ATC_ROT_WARP0) {
         // ------------------------------------------------------------------- RoPE rotation warps
@@ -350,6 +366,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                 uint32_t v0[32];
                 tmem_ld_32x32(t_row + ATC_O_COL + 32 * half, v0);
                 tmem_ld_wait();
+                if (threadIdx.x == 0) ATC_STAMP(18);
                 // read the partner's partial sum BEFORE releasing the tile: once o_empty completes the partner may
                 // run ahead into the next item and overwrite it
                 const float inv_sum = 1.0f / (sum + *peer_sum);
@@ -376,7 +393,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             // one coalesced TMA store per query tile.  The staging rows are rewritten only in the next item's epilogue,
             // which this thread's tile reaches through the max-exchange barrier, i.e. after the wait below.
             fence_proxy_async();
+            if (threadIdx.x == 0) ATC_STAMP(19);
             named_bar_sync(3 + mt, 256);
+            if (threadIdx.x == 0) ATC_STAMP(20);
             if (stamper && mt * 128 < T) {
                 tma_store_3d(mt ? &tmap_o1 : &tmap_o, ostage + mt * 16384, h * 64, mt * 128, f);
                 tma_commit_group();
