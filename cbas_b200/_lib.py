@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcbas_b200.so")
+# CBAS_B200_LIB: load another build of the same library (A/B timing of two kernel versions on one GPU box)
+LIB_PATH = os.environ.get("CBAS_B200_LIB") or os.path.join(_HERE, "libcbas_b200.so")
 
 _lib = None
 _lock = threading.Lock()

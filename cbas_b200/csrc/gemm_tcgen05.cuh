@@ -175,32 +175,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     } else if (warp == kMmaWarp) {
-        if (lane == 0 && cta_rank == 0) {
+        if (cta_rank == 0) {
             // ------------------------------------------------------------ MMA issuer (pair: leader CTA only)
+            // The whole warp runs the loop and one elected lane issues: with warp-uniform control flow the
+            // descriptors live in uniform registers (see elect_one in ptx.cuh).
             constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BLOCK_N);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t a_u = smem_u32(smem_a), b_u = smem_u32(smem_b);
             uint32_t stage = 0, phase = 0;
             int iter = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++iter) {
                 const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                const uint32_t tmem_d = tmem_u + acc * BLOCK_N;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * Cfg::kStageA));
-                    const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::kStageB));
+                    const uint64_t da = umma_desc_sw128(a_u + stage * Cfg::kStageA);
+                    const uint64_t db = umma_desc_sw128(b_u + stage * Cfg::kStageB);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
-                        // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (>>4) address field
-                        if (CG == 1) umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                        else umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
+                            // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (>>4) address field
+                            if (CG == 1) umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            else umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+                        if (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_pair(&empty_bar[stage], 3);
+                        if (kb == k_blocks - 1) {
+                            if (CG == 1) umma_commit(&tmem_full[acc]); else umma_commit_pair(&tmem_full[acc], 3);
+                        }
                     }
-                    // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-                    if (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_pair(&empty_bar[stage], 3);
-                    if (kb == k_blocks - 1) {
-                        if (CG == 1) umma_commit(&tmem_full[acc]); else umma_commit_pair(&tmem_full[acc], 3);
-                    }
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
