@@ -162,23 +162,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == ATC_PRODUCER_WARP) {
-        if (lane == 0) {
-            // ---------------------------------------------------------------- TMA producer
-            int it = 0;
-            for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
-                const int b = it & 1;
-                const int f = w / p.heads, h = w % p.heads;
-                uint8_t* set = smem + b * set_bytes;
-                const int row0 = f * T;
-                mbar_wait(&qk_empty[b], ((it >> 1) & 1) ^ 1);
+        // -------------------------------------------------------------------- TMA producer (one elected lane issues)
+        int it = 0;
+        for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
+            const int b = it & 1;
+            const int f = w / p.heads, h = w % p.heads;
+            uint8_t* set = smem + b * set_bytes;
+            const int row0 = f * T;
+            mbar_wait(&qk_empty[b], ((it >> 1) & 1) ^ 1);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&qk_full[b], 32768 + TK * 128);
                 tma_load_2d(set, &tmap_q, &qk_full[b], h * 64, row0);
                 tma_load_2d(set + 16384, &tmap_q, &qk_full[b], h * 64, row0 + 128);
                 tma_load_2d(set + 32768, &tmap_kv, &qk_full[b], p.D + h * 64, row0);
-                mbar_wait(&v_empty[b], ((it >> 1) & 1) ^ 1);
+            }
+            __syncwarp();
+            mbar_wait(&v_empty[b], ((it >> 1) & 1) ^ 1);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&v_full[b], TK * 128);
                 tma_load_2d(set + 32768 + TK * 128, &tmap_kv, &v_full[b], 2 * p.D + h * 64, row0);
             }
+            __syncwarp();
         }
     } else if (warp == ATC_MMA_WARP0 || warp == ATC_MMA_WARP0 + 1) {
         // -------------------------------------------------------------------- MMA issuer of query tile mt
@@ -396,10 +400,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             if (threadIdx.x == 0) ATC_STAMP(19);
             named_bar_sync(3 + mt, 256);
             if (threadIdx.x == 0) ATC_STAMP(20);
-            if (stamper && mt * 128 < T) {
-                tma_store_3d(mt ? &tmap_o1 : &tmap_o, ostage + mt * 16384, h * 64, mt * 128, f);
-                tma_commit_group();
-                tma_wait_group_read<0>();
+            if ((warp & 7) == 0 && mt * 128 < T) {  // first warp of the tile, uniform operands, elected lane
+                if (elect_one()) {
+                    if (mt) tma_store_3d(&tmap_o1, ostage + 16384, h * 64, 128, f);
+                    else tma_store_3d(&tmap_o, ostage, h * 64, 0, f);
+                    tma_commit_group();
+                    tma_wait_group_read<0>();
+                }
+                __syncwarp();
             }
             if (stamper) ATC_STAMP(sbase + 4);
         }

@@ -148,15 +148,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == kProducerWarp) {
-        if (lane == 0) {
-            // ------------------------------------------------------------ TMA producer
-            uint32_t stage = 0, phase = 0;
-            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-                const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
-                const int a_row = (m_blk * CG + (int)cta_rank) * GEMM_BLOCK_M;
-                const int b_row = n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / CG);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // ---------------------------------------------------------------- TMA producer (whole warp, one elected lane)
+        uint32_t stage = 0, phase = 0;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+            const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+            const int a_row = (m_blk * CG + (int)cta_rank) * GEMM_BLOCK_M;
+            const int b_row = n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / CG);
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     if (CG == 1) {
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
                         tma_load_2d(smem_a + stage * Cfg::kStageA, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, a_row);
@@ -170,8 +170,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         tma_load_2d_pair(smem_b + stage * Cfg::kStageB, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K,
                                          b_row);
                     }
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == kMmaWarp) {
@@ -219,7 +220,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int sub = (ew >> 2) & 1;     // which half of a slab's columns
         const int quarter = warp & 3;      // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
         const int row_in_tile = quarter * 32 + lane;
-        const bool issuer = (ew & 7) == 0 && lane == 0;  // one bulk-store issuer per group
+        const bool issuer_warp = (ew & 7) == 0;  // one bulk-store issuing warp per group (its elected lane issues)
         constexpr int kHalf = kSlabCols / 2;             // columns per thread per slab: 32 (bf16) or 16 (fp32)
         uint8_t* group_slabs = smem_stage + group * Cfg::kSlabsPerGroup * GEMM_SLAB_BYTES;
         const int swz = row_in_tile & 7;
@@ -276,9 +277,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     uint8_t* slab_row = slab + row_in_tile * 128;
                     if (Cfg::kSlabsPerGroup == 2) {
                         sbuf ^= 1;
-                        if (issuer) tma_wait_group_read<1>();
+                        if (issuer_warp && elect_one()) tma_wait_group_read<1>();
                     } else {
-                        if (issuer) tma_wait_group_read<0>();
+                        if (issuer_warp && elect_one()) tma_wait_group_read<0>();
                     }
                     named_bar_sync(1 + group, 256);
 #pragma unroll
@@ -306,11 +307,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                     fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
                     named_bar_sync(1 + group, 256);
-                    if (issuer) {
+                    if (issuer_warp) {
                         const int ns = n_blk * BLOCK_N + s * kSlabCols;
-                        if (EPI == EPI_RESID_F32) tma_reduce_add_2d(&tmap_out, slab, ns, m_base);
-                        else tma_store_2d(&tmap_out, slab, ns, m_base);
-                        tma_commit_group();
+                        if (elect_one()) {
+                            if (EPI == EPI_RESID_F32) tma_reduce_add_2d(&tmap_out, slab, ns, m_base);
+                            else tma_store_2d(&tmap_out, slab, ns, m_base);
+                            tma_commit_group();
+                        }
                     }
                 }
             } else {
@@ -346,7 +349,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
         }
-        if (kStaged && issuer) tma_wait_group<0>();  // all bulk stores of this CTA have landed
+        if (kStaged && issuer_warp && elect_one()) tma_wait_group<0>();  // all bulk stores of this CTA have landed
     }
 
     __syncwarp();
