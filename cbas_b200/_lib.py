@@ -56,10 +56,12 @@ HEAD_WEIGHT_PTRS = (
     "lin0_w", "lin0_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b", "att_w", "att_b",
     "w_ih_f", "w_hh_f", "b_ih_f", "b_hh_f", "w_ih_r", "w_hh_r", "b_ih_r", "b_hh_r",
 )
+HEAD_WEIGHT_PTRS_L1 = ("w_ih_f1", "w_hh_f1", "b_ih_f1", "b_hh_f1", "w_ih_r1", "w_hh_r1", "b_ih_r1", "b_hh_r1")
 
 
 class HeadWeights(C.Structure):
-    _fields_ = [(n, c_void_p) for n in HEAD_WEIGHT_PTRS] + [("gate", c_float), ("attention_temp", c_float)]
+    _fields_ = ([(n, c_void_p) for n in HEAD_WEIGHT_PTRS] + [("gate", c_float), ("attention_temp", c_float)]
+                + [(n, c_void_p) for n in HEAD_WEIGHT_PTRS_L1])
 
 
 # name -> (restype, argtypes); every symbol include/cbas_b200.h declares
@@ -118,7 +120,7 @@ def lib() -> C.CDLL:
                 fn = getattr(handle, name)
                 fn.restype = res
                 fn.argtypes = args
-            if handle.cbas_b200_abi_version() != 1:
+            if handle.cbas_b200_abi_version() != 2:
                 raise RuntimeError("libcbas_b200.so ABI version mismatch; rebuild")
             _lib = handle
     return _lib

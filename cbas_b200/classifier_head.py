@@ -90,11 +90,12 @@ class ClassifierLSTMDeltas(nn.Module):
         if self._native is not None and self._native_key == key:
             return self._native
         self._drop_native()
-        if not self.use_acceleration:
-            raise NotImplementedError("use_acceleration=False heads are not built yet")
+        if self.lstm_hidden_size not in (64, 128) or self.lstm_layers not in (1, 2):
+            raise NotImplementedError("cbas_b200 head: lstm_hidden_size must be 64 or 128 and lstm_layers 1 or 2")
         lib = _lib.lib()
         cfg = _lib.HeadCfg(self.in_features, self.out_features, self.seq_len, self.bottleneck_dim,
-                           self.lstm_hidden_size, self.sw, float(self.ema_alpha), 1, int(self.lstm_layers))
+                           self.lstm_hidden_size, self.sw, float(self.ema_alpha), int(bool(self.use_acceleration)),
+                           int(self.lstm_layers))
         keep = []
 
         def ptr(t: torch.Tensor) -> int:
@@ -105,10 +106,11 @@ class ClassifierLSTMDeltas(nn.Module):
         w = _lib.HeadWeights()
         w.cls_w, w.cls_b = ptr(self.cls_bottleneck[0].weight), ptr(self.cls_bottleneck[0].bias)
         w.delta_w, w.delta_b = ptr(self.delta_bottleneck[0].weight), ptr(self.delta_bottleneck[0].bias)
-        w.acc_w, w.acc_b = ptr(self.acc_bottleneck[0].weight), ptr(self.acc_bottleneck[0].bias)
+        if self.use_acceleration:
+            w.acc_w, w.acc_b = ptr(self.acc_bottleneck[0].weight), ptr(self.acc_bottleneck[0].bias)
+            w.acc_ln_g, w.acc_ln_b = ptr(self.acc_ln.weight), ptr(self.acc_ln.bias)
         w.cls_ln_g, w.cls_ln_b = ptr(self.cls_ln.weight), ptr(self.cls_ln.bias)
         w.delta_ln_g, w.delta_ln_b = ptr(self.delta_ln.weight), ptr(self.delta_ln.bias)
-        w.acc_ln_g, w.acc_ln_b = ptr(self.acc_ln.weight), ptr(self.acc_ln.bias)
         w.lin0_w, w.lin0_b = ptr(self.lin0[0].weight), ptr(self.lin0[0].bias)
         w.lin1_w, w.lin1_b = ptr(self.lin1.weight), ptr(self.lin1.bias)
         w.lin2_w, w.lin2_b = ptr(self.lin2.weight), ptr(self.lin2.bias)
@@ -117,6 +119,11 @@ class ClassifierLSTMDeltas(nn.Module):
         w.b_ih_f, w.b_hh_f = ptr(self.lstm.bias_ih_l0), ptr(self.lstm.bias_hh_l0)
         w.w_ih_r, w.w_hh_r = ptr(self.lstm.weight_ih_l0_reverse), ptr(self.lstm.weight_hh_l0_reverse)
         w.b_ih_r, w.b_hh_r = ptr(self.lstm.bias_ih_l0_reverse), ptr(self.lstm.bias_hh_l0_reverse)
+        if self.lstm_layers == 2:
+            w.w_ih_f1, w.w_hh_f1 = ptr(self.lstm.weight_ih_l1), ptr(self.lstm.weight_hh_l1)
+            w.b_ih_f1, w.b_hh_f1 = ptr(self.lstm.bias_ih_l1), ptr(self.lstm.bias_hh_l1)
+            w.w_ih_r1, w.w_hh_r1 = ptr(self.lstm.weight_ih_l1_reverse), ptr(self.lstm.weight_hh_l1_reverse)
+            w.b_ih_r1, w.b_hh_r1 = ptr(self.lstm.bias_ih_l1_reverse), ptr(self.lstm.bias_hh_l1_reverse)
         w.gate = float(self.gate.detach().cpu())
         w.attention_temp = float(self.attention_temp.detach().cpu())
         handle = C.c_void_p()

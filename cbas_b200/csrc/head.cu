@@ -14,9 +14,15 @@
 //   H4 tcgen05 GEMM       Z = GELU(a W0^T + b0)                      [rows, 256] fp32
 //   H5 head_center_split  z - mean_t z  -> bf16 hi/lo
 //   H6 tcgen05 GEMM       G = z (Wih_f | Wih_r)^T + (b_ih + b_hh)    [rows, 512] fp32  (input half of the gates)
-//   H7 head_lstm_dir      the recurrence: W_hh of one direction resident in shared memory (fp32, 64 KB), each
+//   H7 head_lstm_dir      the recurrence: W_hh of one direction resident in shared memory (fp32, 64 KB; for
+//                         lstm_hidden_size 128 the 256 KB matrix is streamed through L1/L2 instead), each
 //                         warp advances 4 windows at a time (register-tiled, h broadcast from shared memory),
-//                         only the steps that can reach the centre frames are run (21 of 31 per direction)
+//                         only the steps that can reach the centre frames are run (21 of 31 per direction).
+//                         lstm_layers = 2: layer 0 runs all steps, its [fwd|rev] outputs are split to bf16 hi/lo
+//                         and go through one more input-gate GEMM (H6') and recurrence (H7').
+//   use_acceleration = False is the same pipeline with a zero acceleration stream (zero bottleneck / LayerNorm
+//                         parameters and zero lin0 columns give exactly the two-stream concat of
+//                         classifier_head.py:165-167).
 //   H8 head_pool          attention pooling over the centre frames (warp-shuffle reductions), lin2, sigmoid-gate
 //                         lerp with the linear branch, temperature softmax
 //
@@ -37,7 +43,7 @@ namespace {
 
 constexpr int HEAD_BN = 128;    // bottleneck width
 constexpr int HEAD_LIN0 = 256;  // lin0 width = LSTM input width
-constexpr int HEAD_HS = 64;     // LSTM hidden size
+constexpr int HEAD_MAX_HS = 128; // LSTM hidden size: 64 (default) or 128 (the reference's sweep, sweep_runner.py:106)
 constexpr int HEAD_MAX_C = 32;
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
@@ -301,71 +307,77 @@ head_center_split_kernel(const float* __restrict__ Z, int windows, int T, __nv_b
 // Wt[k][unit] float4 (i,f,g,o) = 64 KB, plus per-warp h[k][4 windows].
 constexpr int LSTM_WARPS = 8;
 constexpr int LSTM_WPW = 4;  // windows per warp
-constexpr int LSTM_SMEM = HEAD_HS * HEAD_HS * 16 + LSTM_WARPS * HEAD_HS * LSTM_WPW * 4;
+constexpr int lstm_smem_bytes(int HS, bool resident) {
+    return (resident ? HS * HS * 16 : 0) + LSTM_WARPS * HS * LSTM_WPW * 4;
+}
 
+// RESIDENT: W_hh of this direction lives in shared memory; otherwise it is read through the read-only path every
+// step (HS = 128: 256 KB per direction does not fit next to anything else; all warps of the CTA walk k in step, so
+// the reads are L1 hits after the first warp).
+template <int HS, bool RESIDENT>
 __global__ void __launch_bounds__(LSTM_WARPS * 32)
-head_lstm_dir_kernel(const float* __restrict__ G,        // [windows*T, 512] input gates (fwd | rev), biases included
-                     const float* __restrict__ whh_t,    // [2][64 k][64 unit][4 gate]
+head_lstm_dir_kernel(const float* __restrict__ G,        // [windows*T, 8*HS] input gates (fwd | rev), biases included
+                     const float* __restrict__ whh_t,    // [2][HS k][HS unit][4 gate]
                      int windows, int T, int l, int r,
-                     float* __restrict__ Hout) {         // [windows, r-l, 128] (fwd 64 | rev 64)
+                     float* __restrict__ Hout) {         // [windows, r-l, 2*HS] (fwd | rev)
+    constexpr int UPL = HS / 32;  // hidden units per lane
     extern __shared__ __align__(16) uint8_t lstm_smem[];
-    float4* Wt = reinterpret_cast<float4*>(lstm_smem);                       // [64][64]
-    float* hb_all = reinterpret_cast<float*>(lstm_smem + HEAD_HS * HEAD_HS * 16);
+    float4* Wt = reinterpret_cast<float4*>(lstm_smem);                       // [HS][HS] when RESIDENT
+    float* hb_all = reinterpret_cast<float*>(lstm_smem + (RESIDENT ? HS * HS * 16 : 0));
     const int dir = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    {
-        const float4* src = reinterpret_cast<const float4*>(whh_t) + (long long)dir * HEAD_HS * HEAD_HS;
-        for (int i = threadIdx.x; i < HEAD_HS * HEAD_HS; i += blockDim.x) Wt[i] = __ldg(src + i);
+    const float4* wsrc = reinterpret_cast<const float4*>(whh_t) + (long long)dir * HS * HS;
+    if (RESIDENT) {
+        for (int i = threadIdx.x; i < HS * HS; i += blockDim.x) Wt[i] = __ldg(wsrc + i);
     }
-    float4* hb = reinterpret_cast<float4*>(hb_all + warp * HEAD_HS * LSTM_WPW);  // hb[k] = h of the 4 windows at unit k
-    for (int k = lane; k < HEAD_HS; k += 32) hb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* hb = reinterpret_cast<float4*>(hb_all + warp * HS * LSTM_WPW);  // hb[k] = h of the 4 windows at unit k
+    for (int k = lane; k < HS; k += 32) hb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     const int w_base = (blockIdx.x * LSTM_WARPS + warp) * LSTM_WPW;
     if (w_base >= windows) return;
     const int steps = dir == 0 ? r : T - l;
     const int n_keep = r - l;
-    float c[2][LSTM_WPW];
+    float c[UPL][LSTM_WPW];
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < UPL; ++u)
 #pragma unroll
         for (int w = 0; w < LSTM_WPW; ++w) c[u][w] = 0.f;
 
     for (int s = 0; s < steps; ++s) {
         const int t = dir == 0 ? s : T - 1 - s;
         // input half of the gates (prefetched while the recurrent half is accumulated)
-        float acc[2][4][LSTM_WPW];
+        float acc[UPL][4][LSTM_WPW];
 #pragma unroll
         for (int w = 0; w < LSTM_WPW; ++w) {
             const int win = min(w_base + w, windows - 1);
-            const float* g = G + ((long long)win * T + t) * 512 + dir * 256;
+            const float* g = G + ((long long)win * T + t) * (8 * HS) + dir * 4 * HS;
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < UPL; ++u)
 #pragma unroll
-                for (int gt = 0; gt < 4; ++gt) acc[u][gt][w] = __ldg(g + gt * HEAD_HS + lane + 32 * u);
+                for (int gt = 0; gt < 4; ++gt) acc[u][gt][w] = __ldg(g + gt * HS + lane + 32 * u);
         }
-#pragma unroll 8
-        for (int k = 0; k < HEAD_HS; ++k) {
-            const float4 w0 = Wt[k * HEAD_HS + lane];       // unit lane     : i,f,g,o weights for h_k
-            const float4 w1 = Wt[k * HEAD_HS + lane + 32];  // unit lane + 32
-            const float4 h = hb[k];                          // h_k of the 4 windows (broadcast)
+#pragma unroll 4
+        for (int k = 0; k < HS; ++k) {
+            const float4 h = hb[k];  // h_k of the 4 windows (broadcast)
             const float hv[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
-            for (int w = 0; w < LSTM_WPW; ++w) {
-                acc[0][0][w] = fmaf(w0.x, hv[w], acc[0][0][w]);
-                acc[0][1][w] = fmaf(w0.y, hv[w], acc[0][1][w]);
-                acc[0][2][w] = fmaf(w0.z, hv[w], acc[0][2][w]);
-                acc[0][3][w] = fmaf(w0.w, hv[w], acc[0][3][w]);
-                acc[1][0][w] = fmaf(w1.x, hv[w], acc[1][0][w]);
-                acc[1][1][w] = fmaf(w1.y, hv[w], acc[1][1][w]);
-                acc[1][2][w] = fmaf(w1.z, hv[w], acc[1][2][w]);
-                acc[1][3][w] = fmaf(w1.w, hv[w], acc[1][3][w]);
+            for (int u = 0; u < UPL; ++u) {
+                // unit lane + 32u: i,f,g,o weights for h_k
+                const float4 wv = RESIDENT ? Wt[k * HS + lane + 32 * u] : __ldg(wsrc + k * HS + lane + 32 * u);
+#pragma unroll
+                for (int w = 0; w < LSTM_WPW; ++w) {
+                    acc[u][0][w] = fmaf(wv.x, hv[w], acc[u][0][w]);
+                    acc[u][1][w] = fmaf(wv.y, hv[w], acc[u][1][w]);
+                    acc[u][2][w] = fmaf(wv.z, hv[w], acc[u][2][w]);
+                    acc[u][3][w] = fmaf(wv.w, hv[w], acc[u][3][w]);
+                }
             }
         }
         __syncwarp();  // every lane has read the old h
-        float hn[2][LSTM_WPW];
+        float hn[UPL][LSTM_WPW];
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < UPL; ++u)
 #pragma unroll
             for (int w = 0; w < LSTM_WPW; ++w) {
                 const float ig = sigmoid_f(acc[u][0][w]), fg = sigmoid_f(acc[u][1][w]);
@@ -373,15 +385,15 @@ head_lstm_dir_kernel(const float* __restrict__ G,        // [windows*T, 512] inp
                 c[u][w] = fg * c[u][w] + ig * gg;
                 hn[u][w] = og * tanh_f(c[u][w]);
             }
-        hb[lane] = make_float4(hn[0][0], hn[0][1], hn[0][2], hn[0][3]);
-        hb[lane + 32] = make_float4(hn[1][0], hn[1][1], hn[1][2], hn[1][3]);
+#pragma unroll
+        for (int u = 0; u < UPL; ++u) hb[lane + 32 * u] = make_float4(hn[u][0], hn[u][1], hn[u][2], hn[u][3]);
         if (t >= l && t < r) {
 #pragma unroll
             for (int w = 0; w < LSTM_WPW; ++w) {
                 if (w_base + w < windows) {
-                    float* o = Hout + ((long long)(w_base + w) * n_keep + (t - l)) * 128 + dir * HEAD_HS;
-                    o[lane] = hn[0][w];
-                    o[lane + 32] = hn[1][w];
+                    float* o = Hout + ((long long)(w_base + w) * n_keep + (t - l)) * (2 * HS) + dir * HS;
+#pragma unroll
+                    for (int u = 0; u < UPL; ++u) o[lane + 32 * u] = hn[u][w];
                 }
             }
         }
@@ -389,48 +401,88 @@ head_lstm_dir_kernel(const float* __restrict__ G,        // [windows*T, 512] inp
     }
 }
 
+// fp32 rows -> bf16 [hi | lo | hi] (the A-operand layout of the split GEMMs); K multiple of 4
+__global__ void __launch_bounds__(256)
+head_split_rows_kernel(const float* __restrict__ X, long long rows, int K, __nv_bfloat16* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 per thread
+    const int k4 = K / 4;
+    if (i >= rows * k4) return;
+    const long long row = i / k4;
+    const int k = (int)(i - row * k4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(X + row * K + k);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_bf16(x[j], hi[j], lo[j]);
+    __nv_bfloat16* o = out + row * 3 * K + k;
+    *reinterpret_cast<uint2*>(o) = *reinterpret_cast<uint2*>(hi);
+    *reinterpret_cast<uint2*>(o + K) = *reinterpret_cast<uint2*>(lo);
+    *reinterpret_cast<uint2*>(o + 2 * K) = *reinterpret_cast<uint2*>(hi);
+}
+
 // ---------------------------------------------------------------------------------------------- H8
 struct PoolParams {
-    const float* H;           // [windows, n_keep, 128]
+    const float* H;           // [windows, n_keep, 2*HS]
     const float* lin_logits;  // [windows, C]
     int windows, n_keep, C;
     const float* att_w; float att_b; float inv_att_temp;  // scores / (softplus(attention_temp) + 1e-3)
-    const float* lin2_w; const float* lin2_b;             // [C,128], [C]
+    const float* lin2_w; const float* lin2_b;             // [C, 2*HS], [C]
     float gate_sig;                                       // sigmoid(gate)
     float inv_temperature;                                // 1 / max(1e-3, T)
     float* probs;   // [windows, C] or null
     float* logits;  // [windows, C] or null
-    float* rawm;    // [windows, 128] or null (attended latent, classifier_head.py:145)
+    float* rawm;    // [windows, 2*HS] or null (attended latent, classifier_head.py:145)
 };
 
-// one warp per window; lane owns 4 of the 128 latent channels
+// one warp per window; lane owns CPL = 2*HS/32 consecutive latent channels
+template <int HS>
 __global__ void __launch_bounds__(256)
 head_pool_kernel(const PoolParams p) {
+    constexpr int W2 = 2 * HS, CPL = W2 / 32;
     const int wl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wl >= p.windows) return;
-    const float* h = p.H + (long long)wl * p.n_keep * 128 + lane * 4;
-    const float4 aw = __ldg(reinterpret_cast<const float4*>(p.att_w + lane * 4));
+    const float* h = p.H + (long long)wl * p.n_keep * W2 + lane * CPL;
+    float aw[CPL], rr[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { aw[j] = __ldg(p.att_w + lane * CPL + j); rr[j] = 0.f; }
     // online softmax over the kept steps (classifier_head.py:141-145)
-    float mx = -INFINITY, den = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+    float mx = -INFINITY, den = 0.f;
     for (int t = 0; t < p.n_keep; ++t) {
-        const float4 v = *reinterpret_cast<const float4*>(h + (long long)t * 128);
-        float sc = warp_sum(v.x * aw.x + v.y * aw.y + v.z * aw.z + v.w * aw.w);
+        float v[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; j += 4) {
+            const float4 q = *reinterpret_cast<const float4*>(h + (long long)t * W2 + j);
+            v[j] = q.x; v[j + 1] = q.y; v[j + 2] = q.z; v[j + 3] = q.w;
+        }
+        float part = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) part = fmaf(v[j], aw[j], part);
+        float sc = warp_sum(part);
         sc = (sc + p.att_b) * p.inv_att_temp;
         const float mn = fmaxf(mx, sc);
         const float corr = __expf(mx - mn), e = __expf(sc - mn);
         den = den * corr + e;
-        r0 = r0 * corr + e * v.x; r1 = r1 * corr + e * v.y; r2 = r2 * corr + e * v.z; r3 = r3 * corr + e * v.w;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) rr[j] = rr[j] * corr + e * v[j];
         mx = mn;
     }
     const float inv = 1.0f / den;
-    r0 *= inv; r1 *= inv; r2 *= inv; r3 *= inv;
-    if (p.rawm) *reinterpret_cast<float4*>(p.rawm + (long long)wl * 128 + lane * 4) = make_float4(r0, r1, r2, r3);
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) rr[j] *= inv;
+    if (p.rawm) {
+#pragma unroll
+        for (int j = 0; j < CPL; j += 4)
+            *reinterpret_cast<float4*>(p.rawm + (long long)wl * W2 + lane * CPL + j) =
+                make_float4(rr[j], rr[j + 1], rr[j + 2], rr[j + 3]);
+    }
     // lin2, gate lerp (classifier_head.py:147,171), temperature softmax (cbas.py:545-546)
     float mine = -INFINITY;  // lane c keeps final logit c
     for (int c = 0; c < p.C; ++c) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(p.lin2_w + c * 128 + lane * 4));
-        const float lstm = warp_sum(r0 * w.x + r1 * w.y + r2 * w.z + r3 * w.w) + __ldg(p.lin2_b + c);
+        float part = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) part = fmaf(rr[j], __ldg(p.lin2_w + c * W2 + lane * CPL + j), part);
+        const float lstm = warp_sum(part) + __ldg(p.lin2_b + c);
         const float lin = p.lin_logits[(long long)wl * p.C + c];
         const float fin = lin + p.gate_sig * (lstm - lin);
         if (lane == c) mine = fin;
@@ -531,8 +583,12 @@ struct cbas_head {
     // derived device weights
     __nv_bfloat16* wp = nullptr;    // [384, 3F]
     __nv_bfloat16* w0 = nullptr;    // [256, 1152]
-    __nv_bfloat16* wih = nullptr;   // [512, 768]
-    float *b3 = nullptr, *ln_g = nullptr, *ln_b = nullptr, *b0 = nullptr, *bg = nullptr, *whh_t = nullptr;
+    // per LSTM layer: input-gate weights of both directions [8Hs, 3*K_in] (K_in = 256, then 2Hs), b_ih + b_hh [8Hs],
+    // recurrent weights [2][Hs k][Hs unit][4 gate]
+    __nv_bfloat16* wih[2] = {nullptr, nullptr};
+    float* bg[2] = {nullptr, nullptr};
+    float* whh_t[2] = {nullptr, nullptr};
+    float *b3 = nullptr, *ln_g = nullptr, *ln_b = nullptr, *b0 = nullptr;
     float *lin1_w = nullptr, *lin1_b = nullptr, *lin2_w = nullptr, *lin2_b = nullptr, *att_w = nullptr;
     float att_b = 0.f, inv_att_temp = 1.f, gate_sig = 0.5f;
     // workspace
@@ -543,8 +599,9 @@ struct cbas_head {
     float* q = nullptr;           // [cap, C]
     __nv_bfloat16* A = nullptr;   // [chunk*T, 1152]  (reused as Z' [chunk*T, 768])
     float* Z = nullptr;           // [chunk*T, 256]
-    float* G = nullptr;           // [chunk*T, 512]
-    float* H = nullptr;           // [chunk, r-l, 128]
+    float* G = nullptr;           // [chunk*T, 8Hs]
+    float* H0 = nullptr;          // [chunk*T, 2Hs]   layer-0 outputs of a two-layer LSTM
+    float* H = nullptr;           // [chunk, r-l, 2Hs]
     float* lin = nullptr;         // [chunk, C]
 };
 
@@ -570,13 +627,13 @@ extern "C" {
 int cbas_b200_head_create(const cbas_head_cfg* cfg, const cbas_head_weights* w, cbas_head** out) {
     if (!cfg || !w || !out) return fail("null argument");
     if (cfg->bottleneck != HEAD_BN) return fail("head: bottleneck_dim must be 128");
-    if (cfg->lstm_hidden != HEAD_HS) return fail("head: lstm_hidden_size must be 64 (other sizes: not built yet)");
-    if (cfg->lstm_layers != 1) return fail("head: lstm_layers must be 1 (stacked LSTMs: not built yet)");
-    if (!cfg->use_acceleration) return fail("head: use_acceleration=False is not built yet");
+    if (cfg->lstm_hidden != 64 && cfg->lstm_hidden != 128) return fail("head: lstm_hidden_size must be 64 or 128");
+    if (cfg->lstm_layers != 1 && cfg->lstm_layers != 2) return fail("head: lstm_layers must be 1 or 2");
     if (cfg->in_features % 64 || cfg->in_features <= 0) return fail("head: in_features must be a multiple of 64");
     if (cfg->out_features < 1 || cfg->out_features > HEAD_MAX_C) return fail("head: 1..32 behaviours supported");
     if (cfg->seq_len < 3 || cfg->seq_len % 2 == 0 || cfg->seq_len > 255) return fail("head: seq_len must be odd, 3..255");
-    const int F = cfg->in_features, C = cfg->out_features, T = cfg->seq_len;
+    const int F = cfg->in_features, C = cfg->out_features, T = cfg->seq_len, HS = cfg->lstm_hidden;
+    const bool acc_stream = cfg->use_acceleration != 0;
     auto* h = new cbas_head();
     h->cfg = *cfg;
     const int hsl = T / 2, sw = cfg->center_window;
@@ -590,6 +647,11 @@ int cbas_b200_head_create(const cbas_head_cfg* cfg, const cbas_head_weights* w, 
         std::vector<float> t;
         o.clear();
         for (const float* p : {x, y, z}) {
+            if (p == z && !acc_stream) {
+                // use_acceleration=False: a zero third stream (LayerNorm of a constant row with gamma = beta = 0 is 0)
+                o.insert(o.end(), n, 0.f);
+                continue;
+            }
             if (int e = download(p, n, t)) return e;
             o.insert(o.end(), t.begin(), t.end());
         }
@@ -604,52 +666,65 @@ int cbas_b200_head_create(const cbas_head_cfg* cfg, const cbas_head_weights* w, 
     if (!rc) rc = upload_f32(W, &h->ln_g);
     if (!rc) rc = cat3(w->cls_ln_b, w->delta_ln_b, w->acc_ln_b, HEAD_BN, W);
     if (!rc) rc = upload_f32(W, &h->ln_b);
-    if (!rc) rc = download(w->lin0_w, (size_t)HEAD_LIN0 * 3 * HEAD_BN, W);
+    if (!rc) rc = download(w->lin0_w, (size_t)HEAD_LIN0 * (acc_stream ? 3 : 2) * HEAD_BN, W);
+    if (!rc && !acc_stream) {  // [256, 256] -> [256, 384] with zero columns for the absent stream
+        std::vector<float> P((size_t)HEAD_LIN0 * 3 * HEAD_BN, 0.f);
+        for (int n = 0; n < HEAD_LIN0; ++n)
+            memcpy(&P[(size_t)n * 3 * HEAD_BN], &W[(size_t)n * 2 * HEAD_BN], 2 * HEAD_BN * sizeof(float));
+        W.swap(P);
+    }
     if (!rc) rc = upload_split_weight(W, HEAD_LIN0, 3 * HEAD_BN, &h->w0);
     if (!rc) rc = download(w->lin0_b, HEAD_LIN0, W);
     if (!rc) rc = upload_f32(W, &h->b0);
-    // input-gate weights of both directions stacked, bias = b_ih + b_hh
-    std::vector<float> wf, wr, bif, bhf, bir, bhr;
-    if (!rc) rc = download(w->w_ih_f, (size_t)4 * HEAD_HS * HEAD_LIN0, wf);
-    if (!rc) rc = download(w->w_ih_r, (size_t)4 * HEAD_HS * HEAD_LIN0, wr);
-    if (!rc) {
-        W = wf;
-        W.insert(W.end(), wr.begin(), wr.end());
-        rc = upload_split_weight(W, 8 * HEAD_HS, HEAD_LIN0, &h->wih);
-    }
-    if (!rc) rc = download(w->b_ih_f, 4 * HEAD_HS, bif);
-    if (!rc) rc = download(w->b_hh_f, 4 * HEAD_HS, bhf);
-    if (!rc) rc = download(w->b_ih_r, 4 * HEAD_HS, bir);
-    if (!rc) rc = download(w->b_hh_r, 4 * HEAD_HS, bhr);
-    if (!rc) {
-        W.assign(8 * HEAD_HS, 0.f);
-        for (int i = 0; i < 4 * HEAD_HS; ++i) { W[i] = bif[i] + bhf[i]; W[4 * HEAD_HS + i] = bir[i] + bhr[i]; }
-        rc = upload_f32(W, &h->bg);
-    }
-    // recurrent weights: Wt[dir][k][unit][gate] = W_hh[dir][gate*64 + unit][k]
-    std::vector<float> hf, hr;
-    if (!rc) rc = download(w->w_hh_f, (size_t)4 * HEAD_HS * HEAD_HS, hf);
-    if (!rc) rc = download(w->w_hh_r, (size_t)4 * HEAD_HS * HEAD_HS, hr);
-    if (!rc) {
-        W.assign((size_t)2 * HEAD_HS * HEAD_HS * 4, 0.f);
-        for (int d = 0; d < 2; ++d) {
-            const std::vector<float>& S = d ? hr : hf;
-            for (int k = 0; k < HEAD_HS; ++k)
-                for (int u = 0; u < HEAD_HS; ++u)
-                    for (int g = 0; g < 4; ++g)
-                        W[(((size_t)d * HEAD_HS + k) * HEAD_HS + u) * 4 + g] = S[(size_t)(g * HEAD_HS + u) * HEAD_HS + k];
+    // per layer: input-gate weights of both directions stacked, bias = b_ih + b_hh, recurrent weights re-laid-out
+    for (int layer = 0; layer < cfg->lstm_layers && !rc; ++layer) {
+        const int Kin = layer == 0 ? HEAD_LIN0 : 2 * HS;
+        const float* wif = layer ? w->w_ih_f1 : w->w_ih_f; const float* wir = layer ? w->w_ih_r1 : w->w_ih_r;
+        const float* whf = layer ? w->w_hh_f1 : w->w_hh_f; const float* whr = layer ? w->w_hh_r1 : w->w_hh_r;
+        const float* pbif = layer ? w->b_ih_f1 : w->b_ih_f; const float* pbhf = layer ? w->b_hh_f1 : w->b_hh_f;
+        const float* pbir = layer ? w->b_ih_r1 : w->b_ih_r; const float* pbhr = layer ? w->b_hh_r1 : w->b_hh_r;
+        std::vector<float> wf, wr, bif, bhf, bir, bhr;
+        if (!rc) rc = download(wif, (size_t)4 * HS * Kin, wf);
+        if (!rc) rc = download(wir, (size_t)4 * HS * Kin, wr);
+        if (!rc) {
+            W = wf;
+            W.insert(W.end(), wr.begin(), wr.end());
+            rc = upload_split_weight(W, 8 * HS, Kin, &h->wih[layer]);
         }
-        rc = upload_f32(W, &h->whh_t);
+        if (!rc) rc = download(pbif, 4 * HS, bif);
+        if (!rc) rc = download(pbhf, 4 * HS, bhf);
+        if (!rc) rc = download(pbir, 4 * HS, bir);
+        if (!rc) rc = download(pbhr, 4 * HS, bhr);
+        if (!rc) {
+            W.assign(8 * HS, 0.f);
+            for (int i = 0; i < 4 * HS; ++i) { W[i] = bif[i] + bhf[i]; W[4 * HS + i] = bir[i] + bhr[i]; }
+            rc = upload_f32(W, &h->bg[layer]);
+        }
+        // recurrent weights: Wt[dir][k][unit][gate] = W_hh[dir][gate*Hs + unit][k]
+        std::vector<float> hf, hr;
+        if (!rc) rc = download(whf, (size_t)4 * HS * HS, hf);
+        if (!rc) rc = download(whr, (size_t)4 * HS * HS, hr);
+        if (!rc) {
+            W.assign((size_t)2 * HS * HS * 4, 0.f);
+            for (int d = 0; d < 2; ++d) {
+                const std::vector<float>& S = d ? hr : hf;
+                for (int k = 0; k < HS; ++k)
+                    for (int u = 0; u < HS; ++u)
+                        for (int g = 0; g < 4; ++g)
+                            W[(((size_t)d * HS + k) * HS + u) * 4 + g] = S[(size_t)(g * HS + u) * HS + k];
+            }
+            rc = upload_f32(W, &h->whh_t[layer]);
+        }
     }
     if (!rc) rc = download(w->lin1_w, (size_t)C * F, W);
     if (!rc) rc = upload_f32(W, &h->lin1_w);
     if (!rc) rc = download(w->lin1_b, C, W);
     if (!rc) rc = upload_f32(W, &h->lin1_b);
-    if (!rc) rc = download(w->lin2_w, (size_t)C * 2 * HEAD_HS, W);
+    if (!rc) rc = download(w->lin2_w, (size_t)C * 2 * HS, W);
     if (!rc) rc = upload_f32(W, &h->lin2_w);
     if (!rc) rc = download(w->lin2_b, C, W);
     if (!rc) rc = upload_f32(W, &h->lin2_b);
-    if (!rc) rc = download(w->att_w, 2 * HEAD_HS, W);
+    if (!rc) rc = download(w->att_w, 2 * HS, W);
     if (!rc) rc = upload_f32(W, &h->att_w);
     if (!rc) rc = download(w->att_b, 1, W);
     if (!rc) {
@@ -662,11 +737,12 @@ int cbas_b200_head_create(const cbas_head_cfg* cfg, const cbas_head_weights* w, 
     const size_t rows = (size_t)h->chunk_windows * T;
     if (!rc) rc = check_cuda(cudaMalloc((void**)&h->A, rows * 1152 * 2), "head workspace");
     if (!rc) rc = check_cuda(cudaMalloc((void**)&h->Z, rows * HEAD_LIN0 * 4), "head workspace");
-    if (!rc) rc = check_cuda(cudaMalloc((void**)&h->G, rows * 512 * 4), "head workspace");
-    if (!rc) rc = check_cuda(cudaMalloc((void**)&h->H, (size_t)h->chunk_windows * (h->r - h->l) * 128 * 4), "head workspace");
+    if (!rc) rc = check_cuda(cudaMalloc((void**)&h->G, rows * 8 * HS * 4), "head workspace");
+    if (!rc && cfg->lstm_layers == 2) rc = check_cuda(cudaMalloc((void**)&h->H0, rows * 2 * HS * 4), "head workspace");
+    if (!rc) rc = check_cuda(cudaMalloc((void**)&h->H, (size_t)h->chunk_windows * (h->r - h->l) * 2 * HS * 4), "head workspace");
     if (!rc) rc = check_cuda(cudaMalloc((void**)&h->lin, (size_t)h->chunk_windows * C * 4), "head workspace");
-    if (!rc) rc = check_cuda(cudaFuncSetAttribute(head_lstm_dir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  LSTM_SMEM), "lstm smem attribute");
+    if (!rc) rc = check_cuda(cudaFuncSetAttribute(head_lstm_dir_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  lstm_smem_bytes(64, true)), "lstm smem attribute");
     if (rc) { cbas_b200_head_destroy(h); return rc; }
     *out = h;
     return 0;
@@ -675,8 +751,9 @@ int cbas_b200_head_create(const cbas_head_cfg* cfg, const cbas_head_weights* w, 
 void cbas_b200_head_destroy(cbas_head* h) {
     if (!h) return;
     head_free_ws(h);
-    cudaFree(h->wp); cudaFree(h->w0); cudaFree(h->wih); cudaFree(h->b3); cudaFree(h->ln_g); cudaFree(h->ln_b);
-    cudaFree(h->b0); cudaFree(h->bg); cudaFree(h->whh_t); cudaFree(h->lin1_w); cudaFree(h->lin1_b);
+    cudaFree(h->wp); cudaFree(h->w0); cudaFree(h->b3); cudaFree(h->ln_g); cudaFree(h->ln_b); cudaFree(h->b0);
+    for (int i = 0; i < 2; ++i) { cudaFree(h->wih[i]); cudaFree(h->bg[i]); cudaFree(h->whh_t[i]); }
+    cudaFree(h->H0); cudaFree(h->lin1_w); cudaFree(h->lin1_b);
     cudaFree(h->lin2_w); cudaFree(h->lin2_b); cudaFree(h->att_w);
     cudaFree(h->A); cudaFree(h->Z); cudaFree(h->G); cudaFree(h->H); cudaFree(h->lin);
     delete h;
@@ -731,22 +808,48 @@ static int head_run(cbas_head* h, const void* x_dev, bool x_is_f16, long long n_
             count_launch();
             if (int rc = check_cuda(cudaGetLastError(), "head_center_split_kernel launch")) return rc;
         }
-        {
-            GemmParams p{};
-            p.M = rows; p.N = 512; p.K = 768; p.bias = h->bg; p.out = h->G; p.ldo = 512;
-            if (int rc = launch_gemm(Zs, 768, h->wih, 768, p, EPI_BIAS_F32, s, PROF_HEAD_IH_GEMM)) return rc;
-        }
-        {
+        const int HS = h->cfg.lstm_hidden, layers = h->cfg.lstm_layers;
+        auto run_lstm = [&](int layer, int keep_l, int keep_r, float* Hout) -> int {
             ProfScope prof(PROF_HEAD_LSTM, s);
             const int per_cta = LSTM_WARPS * LSTM_WPW;
             dim3 grid((nw + per_cta - 1) / per_cta, 2);
-            head_lstm_dir_kernel<<<grid, LSTM_WARPS * 32, LSTM_SMEM, s>>>(h->G, h->whh_t, nw, T, h->l, h->r, h->H);
+            if (HS == 64)
+                head_lstm_dir_kernel<64, true><<<grid, LSTM_WARPS * 32, lstm_smem_bytes(64, true), s>>>(
+                    h->G, h->whh_t[layer], nw, T, keep_l, keep_r, Hout);
+            else
+                head_lstm_dir_kernel<128, false><<<grid, LSTM_WARPS * 32, lstm_smem_bytes(128, false), s>>>(
+                    h->G, h->whh_t[layer], nw, T, keep_l, keep_r, Hout);
             count_launch();
-            if (int rc = check_cuda(cudaGetLastError(), "head_lstm_dir_kernel launch")) return rc;
+            return check_cuda(cudaGetLastError(), "head_lstm_dir_kernel launch");
+        };
+        {
+            GemmParams p{};
+            p.M = rows; p.N = 8 * HS; p.K = 768; p.bias = h->bg[0]; p.out = h->G; p.ldo = 8 * HS;
+            if (int rc = launch_gemm(Zs, 768, h->wih[0], 768, p, EPI_BIAS_F32, s, PROF_HEAD_IH_GEMM)) return rc;
+        }
+        if (layers == 2) {
+            // layer 0 over every step, then its [fwd | rev] outputs are the next layer's inputs (nn.LSTM stacking)
+            if (int rc = run_lstm(0, 0, T, h->H0)) return rc;
+            {
+                ProfScope prof(PROF_HEAD_CENTER, s);
+                const long long quads = (long long)rows * (2 * HS / 4);
+                head_split_rows_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, s>>>(h->H0, rows, 2 * HS, h->A);
+                count_launch();
+                if (int rc = check_cuda(cudaGetLastError(), "head_split_rows_kernel launch")) return rc;
+            }
+            GemmParams p{};
+            p.M = rows; p.N = 8 * HS; p.K = 6 * HS; p.bias = h->bg[1]; p.out = h->G; p.ldo = 8 * HS;
+            if (int rc = launch_gemm(h->A, 6 * HS, h->wih[1], 6 * HS, p, EPI_BIAS_F32, s, PROF_HEAD_IH_GEMM)) return rc;
+        }
+        if (int rc = run_lstm(layers - 1, h->l, h->r, h->H)) return rc;
+        {
+            ProfScope prof(PROF_HEAD_LSTM, s);
             PoolParams pp{h->H, h->lin, nw, n_keep, C, h->att_w, h->att_b, h->inv_att_temp, h->lin2_w, h->lin2_b,
                           h->gate_sig, inv_temp, probs_out ? probs_out + w0 * C : nullptr,
-                          logits_out ? logits_out + w0 * C : nullptr, rawm_out ? rawm_out + w0 * 128 : nullptr};
-            head_pool_kernel<<<(nw * 32 + 255) / 256, 256, 0, s>>>(pp);
+                          logits_out ? logits_out + w0 * C : nullptr,
+                          rawm_out ? rawm_out + w0 * 2 * HS : nullptr};
+            if (HS == 64) head_pool_kernel<64><<<(nw * 32 + 255) / 256, 256, 0, s>>>(pp);
+            else head_pool_kernel<128><<<(nw * 32 + 255) / 256, 256, 0, s>>>(pp);
             count_launch();
             if (int rc = check_cuda(cudaGetLastError(), "head_pool_kernel launch")) return rc;
         }

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CBAS_B200_ABI_VERSION 1
+#define CBAS_B200_ABI_VERSION 2
 
 /* preprocessing modes (SURVEY.md 8a rows P / P') */
 #define CBAS_PRE_REFERENCE 0 /* cbas.py:431 + cbas.py:672-675: green/255 replicated x3, native resolution   */
@@ -140,11 +140,11 @@ typedef struct {
     int32_t out_features;  /* C (number of behaviours)   */
     int32_t seq_len;       /* odd window length (31)     */
     int32_t bottleneck;    /* 128                        */
-    int32_t lstm_hidden;   /* 64                         */
+    int32_t lstm_hidden;   /* 64 or 128                  */
     int32_t center_window; /* sw = 5                     */
     float ema_alpha;       /* 0.3                        */
-    int32_t use_acceleration; /* must be 1               */
-    int32_t lstm_layers;      /* must be 1               */
+    int32_t use_acceleration; /* 0: no acceleration stream (acc_* pointers ignored, lin0_w is [256,256]) */
+    int32_t lstm_layers;      /* 1 or 2                  */
 } cbas_head_cfg;
 
 typedef struct {
@@ -154,7 +154,7 @@ typedef struct {
     const float* cls_ln_g; const float* cls_ln_b; /* [128]                             */
     const float* delta_ln_g; const float* delta_ln_b;
     const float* acc_ln_g; const float* acc_ln_b;
-    const float* lin0_w; const float* lin0_b;     /* [256,384], [256]                  */
+    const float* lin0_w; const float* lin0_b;     /* [256,384] ([256,256] without acceleration), [256] */
     const float* lin1_w; const float* lin1_b;     /* [C,F], [C]                        */
     const float* lin2_w; const float* lin2_b;     /* [C,2Hs], [C]                      */
     const float* att_w; const float* att_b;       /* [1,2Hs], [1]                      */
@@ -162,6 +162,9 @@ typedef struct {
     const float* w_ih_r; const float* w_hh_r; const float* b_ih_r; const float* b_hh_r; /* lstm.*_l0_reverse */
     float gate;            /* raw parameter (sigmoid applied inside) */
     float attention_temp;  /* raw parameter (softplus applied inside) */
+    /* second LSTM layer (lstm_layers == 2; input width 2*Hs), else null */
+    const float* w_ih_f1; const float* w_hh_f1; const float* b_ih_f1; const float* b_hh_f1; /* lstm.*_l1         */
+    const float* w_ih_r1; const float* w_hh_r1; const float* b_ih_r1; const float* b_hh_r1; /* lstm.*_l1_reverse */
 } cbas_head_weights;
 
 typedef struct cbas_head cbas_head;

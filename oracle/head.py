@@ -27,7 +27,7 @@ HEAD_KEYS_1LAYER = (
 
 
 def make_head_state(in_features=768, out_features=9, bottleneck=128, lstm_hidden=64, seed=0,
-                    scale=1.0) -> Dict[str, torch.Tensor]:
+                    scale=1.0, lstm_layers=1, use_acceleration=True) -> Dict[str, torch.Tensor]:
     """Deterministic head weights in the reference state_dict layout (workthreads.py:856 model.pth keys),
     drawn from numpy's default_rng so the fixture can be regenerated anywhere without torch's RNG stream.
     Uniform(+-scale/sqrt(fan_in)) like nn.Linear/nn.LSTM defaults; LayerNorm gains jittered around 1."""
@@ -39,20 +39,24 @@ def make_head_state(in_features=768, out_features=9, bottleneck=128, lstm_hidden
 
     Hs, Bn, Fi, Co = lstm_hidden, bottleneck, in_features, out_features
     sd = {"gate": torch.tensor(0.2), "attention_temp": torch.tensor(1.0)}
-    for s in ("cls", "delta", "acc"):
+    streams = ("cls", "delta", "acc") if use_acceleration else ("cls", "delta")
+    for s in streams:
         sd[f"{s}_bottleneck.0.weight"] = u((Bn, Fi), Fi)
         sd[f"{s}_bottleneck.0.bias"] = u((Bn,), Fi)
         sd[f"{s}_ln.weight"] = torch.from_numpy((1.0 + 0.1 * rng.standard_normal(Bn)).astype(np.float32))
         sd[f"{s}_ln.bias"] = torch.from_numpy((0.1 * rng.standard_normal(Bn)).astype(np.float32))
-    sd["lin0.0.weight"], sd["lin0.0.bias"] = u((256, 3 * Bn), 3 * Bn), u((256,), 3 * Bn)
+    aug = len(streams) * Bn
+    sd["lin0.0.weight"], sd["lin0.0.bias"] = u((256, aug), aug), u((256,), aug)
     sd["attention_head.weight"], sd["attention_head.bias"] = u((1, 2 * Hs), 2 * Hs), u((1,), 2 * Hs)
     sd["lin1.weight"], sd["lin1.bias"] = u((Co, Fi), Fi), u((Co,), Fi)
     sd["lin2.weight"], sd["lin2.bias"] = u((Co, 2 * Hs), 2 * Hs), u((Co,), 2 * Hs)
-    for sfx in ("", "_reverse"):
-        sd[f"lstm.weight_ih_l0{sfx}"] = u((4 * Hs, 256), Hs)
-        sd[f"lstm.weight_hh_l0{sfx}"] = u((4 * Hs, Hs), Hs)
-        sd[f"lstm.bias_ih_l0{sfx}"] = u((4 * Hs,), Hs)
-        sd[f"lstm.bias_hh_l0{sfx}"] = u((4 * Hs,), Hs)
+    for layer in range(lstm_layers):  # nn.LSTM: layer k > 0 reads the [fwd | rev] outputs of layer k-1
+        kin = 256 if layer == 0 else 2 * Hs
+        for sfx in ("", "_reverse"):
+            sd[f"lstm.weight_ih_l{layer}{sfx}"] = u((4 * Hs, kin), Hs)
+            sd[f"lstm.weight_hh_l{layer}{sfx}"] = u((4 * Hs, Hs), Hs)
+            sd[f"lstm.bias_ih_l{layer}{sfx}"] = u((4 * Hs,), Hs)
+            sd[f"lstm.bias_hh_l{layer}{sfx}"] = u((4 * Hs,), Hs)
     return sd
 
 
@@ -91,7 +95,8 @@ def _lstm_direction(x: torch.Tensor, w_ih, w_hh, b_ih, b_hh, reverse: bool) -> t
 def head_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, seq_len: int = 31, center_window: int = 5,
                  ema_alpha: float = 0.3, dtype=torch.float32) -> Tuple[torch.Tensor, torch.Tensor]:
     """ClassifierLSTMDeltas.forward in eval mode (classifier_head.py:150-172): x [B,T,F] -> (logits [B,C],
-    rawm [B,2Hs]).  Single-layer bidirectional LSTM, use_acceleration=True."""
+    rawm [B,2Hs]).  The number of LSTM layers, the hidden size and use_acceleration are read off the state dict
+    (as the reference's bundle loader does, workthreads.py:416-425)."""
     p = {k: v.to(dtype) for k, v in sd.items()}
     x = x.to(dtype)
     hsl, sw = seq_len // 2, center_window
@@ -110,15 +115,22 @@ def head_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, seq_len: int = 31
         y = F.gelu(stream @ p[f"{name}_bottleneck.0.weight"].T + p[f"{name}_bottleneck.0.bias"])
         return F.layer_norm(y, (y.shape[-1],), p[f"{name}_ln.weight"], p[f"{name}_ln.bias"], 1e-5)
 
-    aug = torch.cat([bott(cls_s, "cls"), bott(d_s, "delta"), bott(a_s, "acc")], dim=-1)
+    parts = [bott(cls_s, "cls"), bott(d_s, "delta")]
+    if "acc_bottleneck.0.weight" in p:  # use_acceleration (classifier_head.py:163-167)
+        parts.append(bott(a_s, "acc"))
+    aug = torch.cat(parts, dim=-1)
     z = F.gelu(aug @ p["lin0.0.weight"].T + p["lin0.0.bias"])
     z = z - z.mean(dim=1, keepdim=True)
 
-    fwd = _lstm_direction(z, p["lstm.weight_ih_l0"], p["lstm.weight_hh_l0"], p["lstm.bias_ih_l0"],
-                          p["lstm.bias_hh_l0"], False)
-    bwd = _lstm_direction(z, p["lstm.weight_ih_l0_reverse"], p["lstm.weight_hh_l0_reverse"],
-                          p["lstm.bias_ih_l0_reverse"], p["lstm.bias_hh_l0_reverse"], True)
-    out = torch.cat([fwd, bwd], dim=-1)
+    out, layer = z, 0
+    while f"lstm.weight_ih_l{layer}" in p:  # stacked bidirectional layers (nn.LSTM num_layers; no dropout in eval)
+        k = f"_l{layer}"
+        fwd = _lstm_direction(out, p["lstm.weight_ih" + k], p["lstm.weight_hh" + k], p["lstm.bias_ih" + k],
+                              p["lstm.bias_hh" + k], False)
+        bwd = _lstm_direction(out, p["lstm.weight_ih" + k + "_reverse"], p["lstm.weight_hh" + k + "_reverse"],
+                              p["lstm.bias_ih" + k + "_reverse"], p["lstm.bias_hh" + k + "_reverse"], True)
+        out = torch.cat([fwd, bwd], dim=-1)
+        layer += 1
 
     # forward_lstm (classifier_head.py:131-148)
     if l >= r:

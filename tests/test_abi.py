@@ -26,7 +26,7 @@ def test_header_symbols_exported_and_bound():
 
 def test_abi_version_and_error_channel():
     lib = _lib.lib()
-    assert lib.cbas_b200_abi_version() == 1
+    assert lib.cbas_b200_abi_version() == 2
     assert isinstance(lib.cbas_b200_launch_count(), int)
     # argument validation happens before any CUDA call, so this is safe without a GPU
     rc = lib.cbas_b200_encoder_create(None, None, None)
@@ -39,4 +39,4 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.LayerWeights) == 12 * 8
     assert ctypes.sizeof(_lib.EncoderWeights) == 12 * 8
     assert ctypes.sizeof(_lib.HeadCfg) == 9 * 4
-    assert ctypes.sizeof(_lib.HeadWeights) == 28 * 8 + 8
+    assert ctypes.sizeof(_lib.HeadWeights) == 28 * 8 + 8 + 8 * 8  # + the second LSTM layer

@@ -79,6 +79,28 @@ def test_infer_vs_oracle(n, F, C, seq, scale, temp):
     _check_probs(probs.cpu().numpy()[idx], want, f"head F{F} C{C} T{seq} n{n} temp{temp}")
 
 
+@pytest.mark.parametrize("name", ["h128_l2", "h128_l1", "h64_l2_noacc", "h64_l1_noacc"])
+def test_head_variants_fixture_from_reference(golden_dir, name):
+    """Non-default heads (lstm_hidden_size 128, two LSTM layers, no acceleration stream): forward(x) against the
+    reference module's own outputs, and the stride-1 inference path against the oracle."""
+    g = np.load(os.path.join(golden_dir, "head_variants.npz"))
+    hs, layers, acc, seed = (int(v) for v in g[name + ":cfg"])
+    sd = ohead.make_head_state(768, 9, 128, hs, seed=seed, scale=float(g["state_scale"]), lstm_layers=layers,
+                               use_acceleration=bool(acc))
+    x = torch.from_numpy(np.random.default_rng(int(g["x_seed"])).standard_normal((12, 31, 768)).astype(np.float16)).float()
+    head = _head(sd, in_features=768, out_features=9, seq_len=31, lstm_hidden_size=hs, lstm_layers=layers,
+                 use_acceleration=bool(acc))
+    logits, rawm = head(x.cuda())
+    assert logits.shape == (12, 9) and rawm.shape == (12, 2 * hs)
+    np.testing.assert_allclose(logits.cpu().numpy(), g[name + ":logits"], atol=1e-3, rtol=1e-3)
+    np.testing.assert_allclose(rawm.cpu().numpy(), g[name + ":rawm"], atol=1e-3, rtol=1e-3)
+    n = 333
+    emb = (np.random.default_rng(seed).standard_normal((n, 768)) * 1.2).astype(np.float16)
+    probs = head.infer_embeddings(torch.from_numpy(emb).cuda(), temperature=1.7).cpu().numpy()
+    want = ohead.infer_windows(emb, sd, seq_len=31, temperature=1.7)
+    _check_probs(probs, want, f"head variant {name}")
+
+
 @pytest.mark.parametrize("n", [1, 5, 15, 16, 31])
 def test_short_videos_are_all_padding(n):
     sd = ohead.make_head_state(768, 9, 128, 64, seed=3)

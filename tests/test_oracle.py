@@ -41,6 +41,21 @@ def test_head_default_matches_reference_fixture(golden_dir):
     np.testing.assert_allclose(rawm.numpy(), g["rawm"], atol=5e-5, rtol=1e-4)
 
 
+@pytest.mark.parametrize("name", ["h128_l2", "h128_l1", "h64_l2_noacc", "h64_l1_noacc"])
+def test_head_variants_match_reference_fixture(golden_dir, name):
+    """lstm_hidden_size 128 / lstm_layers 2 (the reference's sweep) and use_acceleration=False, against outputs of
+    the reference module itself (oracle/gen_golden_head_variants.py)."""
+    g = _g(golden_dir, "head_variants.npz")
+    hs, layers, acc, seed = (int(v) for v in g[name + ":cfg"])
+    sd = ohead.make_head_state(768, 9, 128, hs, seed=seed, scale=float(g["state_scale"]), lstm_layers=layers,
+                               use_acceleration=bool(acc))
+    x = torch.from_numpy(np.random.default_rng(int(g["x_seed"])).standard_normal((12, 31, 768)).astype(np.float16)).float()
+    logits, rawm = ohead.head_forward(sd, x)
+    assert rawm.shape == (12, 2 * hs)
+    np.testing.assert_allclose(logits.numpy(), g[name + ":logits"], atol=5e-5, rtol=1e-4)
+    np.testing.assert_allclose(rawm.numpy(), g[name + ":rawm"], atol=5e-5, rtol=1e-4)
+
+
 def test_delta_closed_forms():
     # SURVEY 8a row H1: closed forms of the reflect-padded differences
     x = torch.randn(3, 9, 5)
