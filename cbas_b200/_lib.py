@@ -24,7 +24,7 @@ class EncoderCfg(C.Structure):
         ("hidden", c_int32), ("layers", c_int32), ("heads", c_int32), ("intermediate", c_int32),
         ("prefix_tokens", c_int32), ("mode", c_int32), ("in_h", c_int32), ("in_w", c_int32),
         ("side", c_int32), ("max_frames", c_int32), ("ln_eps", c_float),
-        ("resize_taps_y", c_int32), ("resize_taps_x", c_int32),
+        ("resize_taps_y", c_int32), ("resize_taps_x", c_int32), ("patch", c_int32),
     ]
 
 
@@ -39,6 +39,7 @@ class EncoderWeights(C.Structure):
         ("rope_cos", c_void_p), ("rope_sin", c_void_p), ("lnf_g", c_void_p), ("lnf_b", c_void_p),
         ("layers", C.POINTER(LayerWeights)),
         ("rs_ymin", c_void_p), ("rs_wy", c_void_p), ("rs_xmin", c_void_p), ("rs_wx", c_void_p),
+        ("pos_embed", c_void_p),
     ]
 
 

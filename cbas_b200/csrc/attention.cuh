@@ -216,7 +216,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 // bf16 exactly as the dense kernels do, scores go to a warp-private shared-memory row, then softmax and P V run
 // with the same lane layout and the four key groups are summed at the end.
 // q_cls: [frames, D] bf16 (un-rotated: the CLS token is a prefix token); k and v live in the fused QKV buffer.
-constexpr int CLS_ATT_MAX_T = 288;
+constexpr int CLS_ATT_MAX_T = 1024;  // 16 KB of static shared memory for the four warps' score rows
 __global__ void __launch_bounds__(128)
 cls_attention_kernel(const __nv_bfloat16* __restrict__ q_cls, const __nv_bfloat16* __restrict__ qkv,
                      __nv_bfloat16* __restrict__ out, const float* __restrict__ rope_cos,

@@ -71,6 +71,7 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* 
         configured_smem = smem;
     }
     const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
+    if (!cs || !sn) prefix = T;  // no rotary embedding (DINOv2): no token is a "patch token" for the rotation
     attention_kernel<<<frames * heads, ATT_THREADS, smem, s>>>(qkv, out, cs, sn, T, prefix, heads, heads * ATT_HEAD_DIM,
                                                                scale_log2);
     count_launch();
@@ -176,7 +177,7 @@ struct cbas_encoder {
     cbas_encoder_cfg cfg;
     cbas_encoder_weights w;
     std::vector<cbas_layer_weights> layers;
-    int T = 0, Np = 0, Kp = 0;
+    int T = 0, Np = 0, Kp = 0, P = 16, ns = 0;  // tokens, patches, patch-matrix pitch, patch size, patches per side
     // workspace (device)
     __nv_bfloat16* a_patch = nullptr;  // [max*Np, Kp]
     float* h = nullptr;                // [max*T, D]   residual stream
@@ -193,7 +194,32 @@ namespace {
 int encoder_embed(cbas_encoder* e, const uint8_t* frames_u8, const float* planes, int n, long long fs, int rs,
                   cudaStream_t s) {
     const cbas_encoder_cfg& c = e->cfg;
-    if (planes) {
+    if (e->P != 16) {
+        // generic patch size (DINOv2-with-registers, 14 px): per-element kernels, the stage is < 3 % of the step
+        ProfScope prof(PROF_PREPROCESS, s);
+        if (planes || c.mode == CBAS_PRE_REFERENCE) {
+            if (planes && c.mode != CBAS_PRE_REFERENCE)
+                return fail("float-plane input is only defined for REFERENCE preprocessing");
+            const long long total = (long long)n * e->ns * e->P * e->ns;
+            const unsigned grid = (unsigned)((total + 255) / 256);
+            if (planes)
+                preprocess_green_generic_kernel<true><<<grid, 256, 0, s>>>(planes, e->a_patch, n, c.in_h, c.in_w, 0, 0,
+                                                                          e->P, e->ns, e->Kp);
+            else
+                preprocess_green_generic_kernel<false><<<grid, 256, 0, s>>>(frames_u8, e->a_patch, n, c.in_h, c.in_w, fs,
+                                                                           rs, e->P, e->ns, e->Kp);
+        } else {
+            ResizeTaps tp{(const int*)e->w.rs_ymin, (const float*)e->w.rs_wy, (const int*)e->w.rs_xmin,
+                          (const float*)e->w.rs_wx, c.resize_taps_y, c.resize_taps_x};
+            const long long used = (long long)e->ns * e->P;
+            const long long total = (long long)n * used * used;
+            preprocess_resize_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                frames_u8, e->a_patch, n, c.in_h, c.in_w, fs, rs, c.side, tp, make_float3(0.485f, 0.456f, 0.406f),
+                make_float3(1.0f / 0.229f, 1.0f / 0.224f, 1.0f / 0.225f), e->P, e->ns, e->Kp);
+        }
+        count_launch();
+        if (int rc = check_cuda(cudaGetLastError(), "generic preprocess kernel launch")) return rc;
+    } else if (planes) {
         if (c.mode != CBAS_PRE_REFERENCE) return fail("float-plane input is only defined for REFERENCE preprocessing");
         const long long total = (long long)n * c.in_h * (c.in_w / 16);
         preprocess_plane_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(planes, e->a_patch, n, c.in_h, c.in_w);
@@ -219,8 +245,19 @@ int encoder_embed(cbas_encoder* e, const uint8_t* frames_u8, const float* planes
     p.bias = (const float*)e->w.b_patch;
     p.out = e->h; p.ldo = D;
     p.rows_in = e->Np; p.rows_out = e->T; p.prefix = c.prefix_tokens;
-    return launch_gemm(e->a_patch, e->Kp, (const __nv_bfloat16*)e->w.w_patch, e->Kp, p, EPI_PATCH_F32, s,
-                       PROF_PATCH_GEMM);
+    if (int rc = launch_gemm(e->a_patch, e->Kp, (const __nv_bfloat16*)e->w.w_patch, e->Kp, p, EPI_PATCH_F32, s,
+                             PROF_PATCH_GEMM)) return rc;
+    if (e->w.pos_embed) {
+        // learned absolute position embedding (Dinov2WithRegistersEmbeddings.forward: added before the registers are
+        // spliced in, so it lands on the patch rows; the CLS part is already inside prefix row 0)
+        ProfScope prof(PROF_PATCH_GEMM, s);
+        const long long total = (long long)n * e->Np * (D / 4);
+        add_pos_embed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(e->h, (const float*)e->w.pos_embed, n, e->T,
+                                                                            c.prefix_tokens, e->Np, D);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "add_pos_embed_kernel launch");
+    }
+    return 0;
 }
 
 int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
@@ -283,7 +320,7 @@ int encoder_last_layer_cls_only(cbas_encoder* e, int li, int n, cudaStream_t s) 
         const int items = n * c.heads;
         cls_attention_kernel<<<(items * 32 + 127) / 128, 128, 0, s>>>(
             e->cls_q, e->qkv, e->cls_att, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n, T,
-            c.prefix_tokens, c.heads, D, 0.125f * 1.4426950408889634f, tc ? 1 : 0);
+            e->w.rope_cos ? c.prefix_tokens : T, c.heads, D, 0.125f * 1.4426950408889634f, tc ? 1 : 0);
         count_launch();
         if (int rc = check_cuda(cudaGetLastError(), "cls_attention_kernel launch")) return rc;
     }
@@ -309,7 +346,7 @@ int encoder_forward(cbas_encoder* e, const uint8_t* frames_u8, const float* plan
     if (int rc = encoder_embed(e, frames_u8, planes, n, fs, rs, s)) return rc;
     const int L = stop_after_layer >= 0 ? stop_after_layer : e->cfg.layers;
     // only the pooled CLS embedding is wanted: the last block can skip every row that is thrown away
-    const bool prune = g_prune_last_layer && stop_after_layer < 0 && !hidden_out && e->T <= 288 && L >= 1;
+    const bool prune = g_prune_last_layer && stop_after_layer < 0 && !hidden_out && e->T <= CLS_ATT_MAX_T && L >= 1;
     for (int li = 0; li < L; ++li) {
         if (prune && li == L - 1) {
             if (int rc = encoder_last_layer_cls_only(e, li, n, s)) return rc;
@@ -337,7 +374,10 @@ int cbas_b200_encoder_create(const cbas_encoder_cfg* cfg, const cbas_encoder_wei
     if (cfg->hidden != 384 && cfg->hidden != 768 && cfg->hidden != 1024)
         return fail("hidden size must be 384, 768 or 1024 (DINOv3 ViT-S/B/L)");
     if (cfg->intermediate % 128) return fail("intermediate size must be a multiple of 128");
-    if (cfg->side % 16 || cfg->side <= 0) return fail("ViT input side must be a positive multiple of 16");
+    const int P = cfg->patch ? cfg->patch : 16;
+    if (P != 16 && P != 14) return fail("patch size must be 16 (DINOv3) or 14 (DINOv2-with-registers)");
+    if (cfg->side <= 0 || (P == 16 && cfg->side % 16)) return fail("ViT input side must be a positive multiple of 16");
+    if (cfg->side / P < 1) return fail("ViT input side is smaller than one patch");
     if (cfg->mode == CBAS_PRE_REFERENCE && (cfg->in_h != cfg->side || cfg->in_w != cfg->side))
         return fail("REFERENCE preprocessing keeps the native (square) resolution: in_h == in_w == side");
     if (cfg->mode != CBAS_PRE_REFERENCE && cfg->mode != CBAS_PRE_PROCESSOR) return fail("unknown preprocessing mode");
@@ -347,14 +387,21 @@ int cbas_b200_encoder_create(const cbas_encoder_cfg* cfg, const cbas_encoder_wei
     e->w = *w;
     e->layers.assign(w->layers, w->layers + cfg->layers);
     e->w.layers = e->layers.data();
-    const int ns = cfg->side / 16;
+    const int ns = cfg->side / P;  // floor: a stride-P convolution ignores the remainder of the frame
+    e->P = P; e->ns = ns;
     e->Np = ns * ns;
     e->T = e->Np + cfg->prefix_tokens;
-    e->Kp = cfg->mode == CBAS_PRE_REFERENCE ? 256 : 768;
+    if (3 * ((e->T + 15) & ~15) * 128 > 232448) {
+        delete e;
+        return fail("too many tokens per frame: the attention kernels keep a frame's K and V in shared memory (T <= 605)");
+    }
+    e->Kp = ((cfg->mode == CBAS_PRE_REFERENCE ? P * P : 3 * P * P) + 63) & ~63;
     const size_t mt = (size_t)cfg->max_frames * e->T, D = cfg->hidden;
     cudaError_t err = cudaSuccess;
     auto alloc = [&](void** p, size_t bytes) { if (err == cudaSuccess) err = cudaMalloc(p, bytes); };
     alloc((void**)&e->a_patch, (size_t)cfg->max_frames * e->Np * e->Kp * 2);
+    if (err == cudaSuccess && P != 16)  // the padding columns of the patch matrix stay zero for the handle's lifetime
+        err = cudaMemset(e->a_patch, 0, (size_t)cfg->max_frames * e->Np * e->Kp * 2);
     alloc((void**)&e->h, mt * D * 4);
     alloc((void**)&e->xn, mt * D * 2);
     alloc((void**)&e->qkv, mt * 3 * D * 2);

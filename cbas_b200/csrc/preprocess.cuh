@@ -226,4 +226,85 @@ fill_prefix_kernel(float* __restrict__ h, const float* __restrict__ prefix_token
         __ldg(reinterpret_cast<const float4*>(prefix_tokens + (long long)j * D) + d4);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Generic patch sizes (DINOv2-with-registers uses 14-pixel patches: transformers Dinov2WithRegistersPatchEmbeddings,
+// a stride-P Conv2d, so the grid is floor(side / P) and the right / bottom remainder of the frame is not read).
+// The patch-matrix row pitch Kp is P*P (or 3*P*P) rounded up to 64; the padding columns are zeroed once at create.
+// One thread per (frame, patch row, ky, patch column): P pixels in, P bf16 out.
+template <bool PLANE>
+__global__ void __launch_bounds__(256)
+preprocess_green_generic_kernel(const void* __restrict__ src, __nv_bfloat16* __restrict__ A, int n_frames, int H, int W,
+                                long long frame_stride, int row_stride, int P, int ns, int Kp) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n_frames * ns * P * ns;
+    if (idx >= total) return;
+    const int px = (int)(idx % ns);
+    long long r = idx / ns;
+    const int ky = (int)(r % P); r /= P;
+    const int py = (int)(r % ns);
+    const int f = (int)(r / ns);
+    const int y = py * P + ky, x0 = px * P;
+    __nv_bfloat16* dst = A + ((long long)f * ns * ns + (long long)py * ns + px) * Kp + ky * P;
+    if (PLANE) {
+        const float* g = reinterpret_cast<const float*>(src) + ((long long)f * H + y) * W + x0;
+        for (int kx = 0; kx < P; ++kx) dst[kx] = __float2bfloat16_rn(g[kx] * 255.0f);
+    } else {
+        const uint8_t* g = reinterpret_cast<const uint8_t*>(src) + (long long)f * frame_stride + (long long)y * row_stride +
+                           x0 * 3 + 1;  // green
+        for (int kx = 0; kx < P; ++kx) dst[kx] = __float2bfloat16_rn((float)g[3 * kx]);
+    }
+}
+
+// PROCESSOR mode for any patch size: one thread per output pixel (all three channels), separable antialiased
+// bilinear taps exactly as preprocess_resize_kernel applies them, ImageNet normalisation, scatter into the patch
+// matrix A[frame*Np + py*ns + px][c*P*P + ky*P + kx].
+__global__ void __launch_bounds__(256)
+preprocess_resize_generic_kernel(const uint8_t* __restrict__ frames, __nv_bfloat16* __restrict__ A, int n_frames, int H,
+                                 int W, long long frame_stride, int row_stride, int S, ResizeTaps tp, float3 mean,
+                                 float3 istd, int P, int ns, int Kp) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int used = ns * P;  // pixels of the resized image that fall inside the patch grid
+    const long long total = (long long)n_frames * used * used;
+    if (idx >= total) return;
+    const int x = (int)(idx % used);
+    const int y = (int)((idx / used) % used);
+    const int f = (int)(idx / ((long long)used * used));
+    const uint8_t* img = frames + (long long)f * frame_stride;
+    const int y0 = tp.ymin[y], x0 = tp.xmin[x];
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int j = 0; j < tp.taps_y; ++j) {
+        const float wy = tp.wy[y * tp.taps_y + j];
+        if (wy == 0.f) continue;
+        const int sy = min(y0 + j, H - 1);
+        const uint8_t* row = img + (long long)sy * row_stride;
+        float h[3] = {0.f, 0.f, 0.f};
+        for (int i = 0; i < tp.taps_x; ++i) {
+            const float wx = tp.wx[x * tp.taps_x + i];
+            const int sx = min(x0 + i, W - 1);
+            h[0] = fmaf(wx, (float)row[3 * sx], h[0]);
+            h[1] = fmaf(wx, (float)row[3 * sx + 1], h[1]);
+            h[2] = fmaf(wx, (float)row[3 * sx + 2], h[2]);
+        }
+        acc[0] = fmaf(wy, h[0], acc[0]); acc[1] = fmaf(wy, h[1], acc[1]); acc[2] = fmaf(wy, h[2], acc[2]);
+    }
+    const float mu[3] = {mean.x, mean.y, mean.z}, is[3] = {istd.x, istd.y, istd.z};
+    __nv_bfloat16* dst = A + ((long long)f * ns * ns + (long long)(y / P) * ns + x / P) * Kp + (y % P) * P + (x % P);
+    for (int c = 0; c < 3; ++c) dst[c * P * P] = __float2bfloat16_rn((acc[c] * (1.0f / 255.0f) - mu[c]) * is[c]);
+}
+
+// h[(f*T + prefix + p), :] += pos[p, :]   (learned absolute position embedding of the patch tokens)
+__global__ void __launch_bounds__(256)
+add_pos_embed_kernel(float* __restrict__ h, const float* __restrict__ pos, int n_frames, int T, int prefix, int Np,
+                     int D) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int d4 = D / 4;
+    if (idx >= (long long)n_frames * Np * d4) return;
+    const int c = (int)(idx % d4);
+    const int pidx = (int)((idx / d4) % Np);
+    const int f = (int)(idx / ((long long)d4 * Np));
+    float4* dst = reinterpret_cast<float4*>(h + ((long long)f * T + prefix + pidx) * D) + c;
+    const float4 a = *dst, b = __ldg(reinterpret_cast<const float4*>(pos + (long long)pidx * D) + c);
+    *dst = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
 }  // namespace cbas

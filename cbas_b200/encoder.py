@@ -32,6 +32,12 @@ ARCHITECTURES: Dict[str, Dict[str, int]] = {
     "vits16": dict(hidden_size=384, num_hidden_layers=12, num_attention_heads=6, intermediate_size=1536),
     "vitb16": dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072),
     "vitl16": dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096),
+    # DINOv2-with-registers (CBAS's default encoder, cbas.py:1030-1033): 14-pixel patches, learned absolute position
+    # embedding trained on a 37x37 grid (518 px), no RoPE, layer_norm_eps 1e-6
+    "dinov2reg-s14": dict(hidden_size=384, num_hidden_layers=12, num_attention_heads=6, intermediate_size=1536,
+                          patch_size=14, layer_norm_eps=1e-6, family="dinov2_with_registers", pos_grid=37),
+    "dinov2reg-b14": dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+                          patch_size=14, layer_norm_eps=1e-6, family="dinov2_with_registers", pos_grid=37),
 }
 
 
@@ -45,9 +51,22 @@ class ViTConfig:
     patch_size: int = 16
     layer_norm_eps: float = 1e-5
     rope_theta: float = 100.0
+    family: str = "dinov3_vit"   # or "dinov2_with_registers"
+    pos_grid: int = 0            # dinov2: side of the trained position-embedding grid
 
     @classmethod
     def from_hf(cls, cfg) -> "ViTConfig":
+        if getattr(cfg, "model_type", "dinov3_vit") == "dinov2_with_registers":
+            if getattr(cfg, "use_swiglu_ffn", False):
+                raise ValueError("SwiGLU DINOv2 variants (giant) are not supported by the B200 encoder")
+            if getattr(cfg, "hidden_act", "gelu") != "gelu" or not getattr(cfg, "qkv_bias", True):
+                raise ValueError("only hidden_act='gelu' with qkv_bias is supported")
+            if int(cfg.patch_size) not in (14, 16) or int(cfg.num_channels) != 3:
+                raise ValueError("only 14- or 16-pixel patches on 3-channel input are supported")
+            size = cfg.image_size if isinstance(cfg.image_size, int) else cfg.image_size[0]
+            return cls(cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads,
+                       int(cfg.hidden_size * cfg.mlp_ratio), cfg.num_register_tokens, int(cfg.patch_size),
+                       float(cfg.layer_norm_eps), 0.0, "dinov2_with_registers", size // int(cfg.patch_size))
         if getattr(cfg, "use_gated_mlp", False):
             raise ValueError("gated-MLP DINOv3 variants are not supported by the B200 encoder")
         if getattr(cfg, "hidden_act", "gelu") != "gelu":
@@ -116,7 +135,7 @@ def synthetic_state_dict(cfg: ViTConfig, seed: int = 0) -> Dict[str, torch.Tenso
     sd = {
         "embeddings.cls_token": tn(1, 1, D),
         "embeddings.register_tokens": tn(1, cfg.num_register_tokens, D),
-        "embeddings.patch_embeddings.weight": tn(D, 3, 16, 16),
+        "embeddings.patch_embeddings.weight": tn(D, 3, cfg.patch_size, cfg.patch_size),
         "embeddings.patch_embeddings.bias": torch.zeros(D),
         "norm.weight": torch.ones(D), "norm.bias": torch.zeros(D),
     }
@@ -127,13 +146,50 @@ def synthetic_state_dict(cfg: ViTConfig, seed: int = 0) -> Dict[str, torch.Tenso
             p + "norm2.weight": torch.ones(D), p + "norm2.bias": torch.zeros(D),
             p + "attention.q_proj.weight": tn(D, D), p + "attention.q_proj.bias": torch.zeros(D),
             p + "attention.k_proj.weight": tn(D, D),
+            **({p + "attention.k_proj.bias": torch.zeros(D)} if cfg.family == "dinov2_with_registers" else {}),
             p + "attention.v_proj.weight": tn(D, D), p + "attention.v_proj.bias": torch.zeros(D),
             p + "attention.o_proj.weight": tn(D, D), p + "attention.o_proj.bias": torch.zeros(D),
             p + "layer_scale1.lambda1": torch.ones(D), p + "layer_scale2.lambda1": torch.ones(D),
             p + "mlp.up_proj.weight": tn(I, D), p + "mlp.up_proj.bias": torch.zeros(I),
             p + "mlp.down_proj.weight": tn(D, I), p + "mlp.down_proj.bias": torch.zeros(D),
         })
+    if cfg.family == "dinov2_with_registers":
+        sd["embeddings.position_embeddings"] = tn(1, 1 + cfg.pos_grid * cfg.pos_grid, D)
     return sd
+
+
+def normalize_state_dict(sd: Dict[str, torch.Tensor], family: str) -> Dict[str, torch.Tensor]:
+    """Map a transformers Dinov2WithRegistersModel state dict onto the DINOv3 key names the packer below reads
+    (modeling_dinov2_with_registers.py: query/key/value, output.dense, mlp.fc1/fc2, layernorm)."""
+    if family != "dinov2_with_registers" or "norm.weight" in sd:
+        return sd
+    out = {}
+    for k, v in sd.items():
+        k = k.replace("embeddings.patch_embeddings.projection.", "embeddings.patch_embeddings.")
+        k = k.replace("encoder.layer.", "model.layer.")
+        for a, b in (("attention.attention.query.", "attention.q_proj."), ("attention.attention.key.", "attention.k_proj."),
+                     ("attention.attention.value.", "attention.v_proj."), ("attention.output.dense.", "attention.o_proj."),
+                     ("mlp.fc1.", "mlp.up_proj."), ("mlp.fc2.", "mlp.down_proj.")):
+            k = k.replace(a, b)
+        if k.startswith("layernorm."):
+            k = "norm." + k[len("layernorm."):]
+        out[k] = v
+    return out
+
+
+def interpolate_pos_embed(pos: torch.Tensor, n_h: int, n_w: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Dinov2WithRegistersEmbeddings.interpolate_pos_encoding (modeling_dinov2_with_registers.py:93-145):
+    pos [1, 1+G*G, D] -> (class position [D], patch positions [n_h*n_w, D]); bicubic, antialiased, fp32, and no
+    resampling at all when the grid already matches."""
+    pos = pos.float()
+    cls_pos, patch_pos = pos[0, 0], pos[0, 1:]
+    G = int(round(patch_pos.shape[0] ** 0.5))
+    if G * G == n_h * n_w and n_h == n_w:
+        return cls_pos, patch_pos
+    D = pos.shape[-1]
+    grid = patch_pos.reshape(1, G, G, D).permute(0, 3, 1, 2)
+    grid = nn.functional.interpolate(grid, size=(n_h, n_w), mode="bicubic", align_corners=False, antialias=True)
+    return cls_pos, grid.permute(0, 2, 3, 1).reshape(n_h * n_w, D)
 
 
 class _NativeEncoder:
@@ -153,16 +209,26 @@ class _NativeEncoder:
             return t.data_ptr()
 
         f32, bf16 = torch.float32, torch.bfloat16
+        sd = normalize_state_dict(sd, cfg.family)
+        P = cfg.patch_size
         wp = sd["embeddings.patch_embeddings.weight"].float()
         if mode == PRE_REFERENCE:
             # three identical channels of G/255 (cbas.py:431,674)  ==  one channel against sum_c W / 255
-            w_patch = (wp.sum(dim=1) / 255.0).reshape(D, 256)
+            w_patch = (wp.sum(dim=1) / 255.0).reshape(D, P * P)
         else:
-            w_patch = wp.reshape(D, 768)
+            w_patch = wp.reshape(D, 3 * P * P)
+        kp = (w_patch.shape[1] + 63) // 64 * 64  # GEMM K granularity; the library zero-pads the patch matrix alike
+        if kp != w_patch.shape[1]:
+            w_patch = torch.cat([w_patch, torch.zeros(D, kp - w_patch.shape[1])], dim=1)
         prefix = torch.cat([sd["embeddings.cls_token"].reshape(1, D),
-                            sd["embeddings.register_tokens"].reshape(-1, D)], dim=0).float()
-        n_side = side // 16
-        cos, sin = rope_tables(n_side, n_side, D // cfg.num_attention_heads, cfg.rope_theta)
+                            sd["embeddings.register_tokens"].reshape(-1, D)], dim=0).float().clone()
+        n_side = side // P  # floor, like the stride-P convolution
+        pos_patch = None
+        if cfg.family == "dinov2_with_registers":
+            cls_pos, pos_patch = interpolate_pos_embed(sd["embeddings.position_embeddings"], n_side, n_side)
+            prefix[0] += cls_pos  # the CLS token gets its position before the registers are spliced in
+        else:
+            cos, sin = rope_tables(n_side, n_side, D // cfg.num_attention_heads, cfg.rope_theta)
 
         layers = (_lib.LayerWeights * cfg.num_hidden_layers)()
         for i in range(cfg.num_hidden_layers):
@@ -190,7 +256,10 @@ class _NativeEncoder:
         w = _lib.EncoderWeights()
         w.w_patch, w.b_patch = dev(w_patch, bf16), dev(sd["embeddings.patch_embeddings.bias"], f32)
         w.prefix = dev(prefix, f32)
-        w.rope_cos, w.rope_sin = dev(cos, f32), dev(sin, f32)
+        if pos_patch is None:
+            w.rope_cos, w.rope_sin = dev(cos, f32), dev(sin, f32)
+        else:
+            w.pos_embed = dev(pos_patch, f32)
         w.lnf_g, w.lnf_b = dev(sd["norm.weight"], f32), dev(sd["norm.bias"], f32)
         w.layers = C.cast(layers, C.POINTER(_lib.LayerWeights))
         taps_y = taps_x = 0
@@ -202,7 +271,7 @@ class _NativeEncoder:
             w.rs_xmin, w.rs_wx = dev(torch.from_numpy(xmin), torch.int32), dev(torch.from_numpy(wx), f32)
         c = _lib.EncoderCfg(D, cfg.num_hidden_layers, cfg.num_attention_heads, cfg.intermediate_size,
                             1 + cfg.num_register_tokens, mode, in_hw[0], in_hw[1], side, max_frames,
-                            cfg.layer_norm_eps, taps_y, taps_x)
+                            cfg.layer_norm_eps, taps_y, taps_x, P)
         handle = C.c_void_p()
         with torch.cuda.device(device):
             _lib.check(self.lib.cbas_b200_encoder_create(C.byref(c), C.byref(w), C.byref(handle)), "encoder_create")

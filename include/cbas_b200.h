@@ -54,6 +54,8 @@ typedef struct {
     int32_t max_frames;    /* largest n a forward call may pass (workspace is sized for it)           */
     float ln_eps;
     int32_t resize_taps_y, resize_taps_x; /* PROCESSOR only */
+    int32_t patch;         /* patch size in pixels: 16 (DINOv3; 0 means 16) or 14 (DINOv2-with-registers).  The grid is
+                              floor(side / patch) patches per side, like the stride-`patch` Conv2d it replaces        */
 } cbas_encoder_cfg;
 
 typedef struct {
@@ -66,13 +68,18 @@ typedef struct {
 } cbas_layer_weights;
 
 typedef struct {
-    const void* w_patch; const void* b_patch; /* bf16 [D,Kp] (Kp = 256 REFERENCE-folded, 768 PROCESSOR), f32 [D] */
+    const void* w_patch; const void* b_patch; /* bf16 [D,Kp], f32 [D].  Kp = patch^2 (REFERENCE: channels folded) or
+                                                 3*patch^2 (PROCESSOR), rounded up to a multiple of 64, zero padded */
     const void* prefix;                       /* f32 [prefix_tokens, D]: cls_token then register_tokens */
-    const void* rope_cos; const void* rope_sin; /* f32 [(side/16)^2, 32]                                */
+    const void* rope_cos; const void* rope_sin; /* f32 [Np, 32], or both null: no rotary embedding (DINOv2)  */
     const void* lnf_g; const void* lnf_b;     /* f32 [D] final norm                                    */
     const cbas_layer_weights* layers;         /* host array [L]                                        */
     /* PROCESSOR mode resize taps (device): first source index + normalised weights per output coordinate */
     const void* rs_ymin; const void* rs_wy; const void* rs_xmin; const void* rs_wx;
+    /* learned absolute position embedding of the patch tokens, f32 [Np, D], already interpolated to this grid
+     * (Dinov2WithRegistersEmbeddings.interpolate_pos_encoding), or null (DINOv3).  The CLS position is folded into
+     * prefix row 0 by the host. */
+    const void* pos_embed;
 } cbas_encoder_weights;
 
 typedef struct cbas_encoder cbas_encoder;

@@ -46,6 +46,36 @@ def build_hf_model(arch: str = "vitb16", seed: int = 0, init_scale: float = 1.0,
     return model
 
 
+ARCH_DINOV2 = {
+    "dinov2reg-s14": dict(hidden_size=384, num_hidden_layers=12, num_attention_heads=6),
+    "dinov2reg-b14": dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12),
+}
+
+
+def build_hf_dinov2_model(arch: str = "dinov2reg-b14", seed: int = 0, init_scale: float = 1.0, **overrides):
+    """Random-init transformers Dinov2WithRegistersModel with the geometry of facebook/dinov2-with-registers-*
+    (patch 14, image_size 518 => 37x37 learned position grid, 4 register tokens) - CBAS's default encoder
+    (cbas.py:1030-1033).  The reference calls it exactly like the DINOv3 model (cbas.py:672-677)."""
+    from transformers import Dinov2WithRegistersConfig, Dinov2WithRegistersModel
+    kw = dict(ARCH_DINOV2[arch], patch_size=14, image_size=518, num_register_tokens=4)
+    kw.update(overrides)
+    torch.manual_seed(seed)
+    model = Dinov2WithRegistersModel(Dinov2WithRegistersConfig(**kw)).eval()
+    with torch.no_grad():
+        # the default init leaves register tokens at zero and position embeddings at N(0,1): keep the latter small
+        # enough that the patch content still matters, and give the registers something to carry
+        model.embeddings.register_tokens.normal_(0.0, 0.02)
+        model.embeddings.position_embeddings.mul_(0.02)
+        model.embeddings.cls_token.mul_(0.02)
+        if init_scale != 1.0:
+            for name, p in model.named_parameters():
+                if name.endswith("weight") and p.dim() >= 2:
+                    p.mul_(init_scale)
+    for p in model.parameters():
+        p.requires_grad_(False)
+    return model
+
+
 def preprocess_reference(frames_u8: np.ndarray) -> torch.Tensor:
     """(n,H,W,3) uint8 RGB -> (n,3,H,W) float32: green/255 replicated (cbas.py:431,672-675)."""
     x = torch.from_numpy(frames_u8[:, :, :, 1] / 255.0).float()
@@ -77,6 +107,13 @@ def hidden_states(model, pixel_values: torch.Tensor) -> List[torch.Tensor]:
     """Residual stream after the embeddings and after each block (before the final norm):
     the per-layer taps the GPU parity test compares against."""
     emb = model.embeddings(pixel_values)
+    if not hasattr(model, "rope_embeddings"):  # Dinov2WithRegistersModel: absolute positions, plain layer stack
+        hs, h = [emb], emb
+        for layer in model.encoder.layer:
+            h = layer(h)
+            h = h[0] if isinstance(h, tuple) else h
+            hs.append(h)
+        return hs
     pos = model.rope_embeddings(pixel_values)
     hs = [emb]
     h = emb

@@ -35,8 +35,8 @@ def test_abi_version_and_error_channel():
 
 def test_struct_layouts_match_header():
     # sizes the C compiler produces for the header's structs (LP64): guards against field drift
-    assert ctypes.sizeof(_lib.EncoderCfg) == 13 * 4
+    assert ctypes.sizeof(_lib.EncoderCfg) == 14 * 4
     assert ctypes.sizeof(_lib.LayerWeights) == 12 * 8
-    assert ctypes.sizeof(_lib.EncoderWeights) == 12 * 8
+    assert ctypes.sizeof(_lib.EncoderWeights) == 13 * 8
     assert ctypes.sizeof(_lib.HeadCfg) == 9 * 4
     assert ctypes.sizeof(_lib.HeadWeights) == 28 * 8 + 8 + 8 * 8  # + the second LSTM layer

@@ -74,6 +74,54 @@ def test_processor_mode_parity():
     assert cos >= 0.999 and rel <= 2e-2 and nn_ok
 
 
+@pytest.mark.parametrize("arch,side,n,layers,trained_px", [
+    ("dinov2reg-s14", 112, 5, 12, 518), ("dinov2reg-b14", 256, 3, 12, 518), ("dinov2reg-s14", 256, 2, 4, 252)])
+def test_dinov2_with_registers_parity(arch, side, n, layers, trained_px):
+    """CBAS's default encoder family (cbas.py:1030-1033): 14-px patches (floor(256/14) = 18 per side, the last 4
+    pixels unused), learned position embedding interpolated bicubic+antialias from the 37x37 training grid (used
+    as stored when the grid already matches: trained_px 252 = 18 patches), no RoPE, biased keys - through the same DinoEncoder call as the reference makes (cbas.py:672-677)."""
+    model = oenc.build_hf_dinov2_model(arch, seed=2, init_scale=3.0, num_hidden_layers=layers, image_size=trained_px)
+    frames = oenc.synthetic_frames(n, side, side, seed=15)
+    want = oenc.encode(model, frames, mode="reference")
+    enc = DinoEncoder.from_hf_model(model, "cuda", max_frames=8)
+    fd = torch.from_numpy(frames).cuda()
+    hs = oenc.hidden_states(model, oenc.preprocess_reference(frames))
+    for li in sorted({0, 1, len(hs) - 1}):
+        got = enc.debug_hidden(fd, li).cpu()
+        r = rel_err(got, hs[li])
+        print(f"[parity] {arch}@{side} residual stream after {li} blocks: max|d|/max|ref| {r:.3e}")
+        assert r < 2e-2, f"layer tap {li}"
+    got = enc.encode_u8(fd).cpu()
+    cos, nn_ok, rel = _report(f"{arch}@{side} reference-mode", got, want)
+    assert cos >= 0.999 and rel <= 2e-2 and nn_ok
+    x = torch.from_numpy(frames[:, :, :, 1] / 255.0).float().unsqueeze(1)
+    assert rel_err(enc(x).squeeze(1).cpu(), got) < 1e-5
+
+
+def test_dinov2_against_reference_encode_file_fixture(golden_dir):
+    """_cls.h5 contents the reference's own encode_file produced with a DINOv2-with-registers model
+    (oracle/gen_golden_dinov2.py)."""
+    g = np.load(os.path.join(golden_dir, "encode_file_dinov2reg.npz"))
+    side = int(g["side"])
+    frames = oenc.synthetic_frames(5, side, side, seed=int(g["frames_seed"]))
+    model = oenc.build_hf_dinov2_model("dinov2reg-b14", seed=int(g["model_seed"]), init_scale=float(g["init_scale"]),
+                                       num_hidden_layers=int(g["layers"]))
+    enc = DinoEncoder.from_hf_model(model, "cuda", max_frames=8)
+    got = enc.encode_u8(torch.from_numpy(frames).cuda()).cpu()
+    cos, nn_ok, rel = _report("fixture encode_file, dinov2-with-registers (reference run)", got, g["cls"].astype(np.float32))
+    assert cos >= 0.999 and rel <= 2e-2 and nn_ok
+
+
+def test_dinov2_with_registers_processor_mode():
+    model = oenc.build_hf_dinov2_model("dinov2reg-s14", seed=3, init_scale=3.0, num_hidden_layers=6)
+    frames = oenc.synthetic_frames(3, 256, 256, seed=16)
+    want = oenc.encode(model, frames, mode="processor", size=224)
+    enc = DinoEncoder.from_hf_model(model, "cuda", preprocess="processor", image_size=224, max_frames=8)
+    got = enc.encode_u8(torch.from_numpy(frames).cuda()).cpu()
+    cos, nn_ok, rel = _report("dinov2reg-s14 processor 256->224", got, want)
+    assert cos >= 0.999 and rel <= 2e-2 and nn_ok
+
+
 def test_against_reference_encode_file_fixture(golden_dir):
     g = np.load(os.path.join(golden_dir, "encode_file_vitb.npz"))
     frames = oenc.synthetic_frames(6, 64, 64, seed=int(g["frames_seed"]))

@@ -124,6 +124,38 @@ def test_encoder_oracle_matches_reference_encode_file(golden_dir):
     assert np.abs(c).max() > 0.05
 
 
+def test_dinov2_oracle_matches_reference_encode_file(golden_dir):
+    g = _g(golden_dir, "encode_file_dinov2reg.npz")
+    side = int(g["side"])
+    frames = oenc.synthetic_frames(5, side, side, seed=int(g["frames_seed"]))
+    model = oenc.build_hf_dinov2_model("dinov2reg-b14", seed=int(g["model_seed"]), init_scale=float(g["init_scale"]),
+                                       num_hidden_layers=int(g["layers"]))
+    emb = oenc.encode(model, frames, mode="reference")
+    ref = g["cls"].astype(np.float32)
+    np.testing.assert_allclose(emb.astype(np.float16).astype(np.float32), ref, atol=2e-3, rtol=2e-3)
+    assert np.abs(emb - emb.mean(0, keepdims=True)).max() > 0.05
+
+
+def test_dinov2_state_dict_mapping_and_pos_embed():
+    """Host-side packing of a Dinov2WithRegistersModel: key renaming and the position-embedding interpolation are
+    the transformers implementation's own (no resampling when the grid matches)."""
+    from cbas_b200 import encoder as benc
+    model = oenc.build_hf_dinov2_model("dinov2reg-s14", seed=1, num_hidden_layers=2)
+    cfg = benc.ViTConfig.from_hf(model.config)
+    assert (cfg.family, cfg.patch_size, cfg.pos_grid, cfg.intermediate_size) == ("dinov2_with_registers", 14, 37, 1536)
+    sd = benc.normalize_state_dict(dict(model.state_dict()), cfg.family)
+    for k in ("embeddings.patch_embeddings.weight", "model.layer.1.attention.k_proj.bias", "model.layer.0.mlp.up_proj.weight",
+              "model.layer.1.attention.o_proj.weight", "norm.weight", "embeddings.position_embeddings"):
+        assert k in sd, k
+    x = torch.zeros(1, 3, 256, 256)
+    want = model.embeddings.interpolate_pos_encoding(torch.zeros(1, 1 + 18 * 18, 384), 256, 256)
+    cls_pos, patch_pos = benc.interpolate_pos_embed(sd["embeddings.position_embeddings"], 18, 18)
+    np.testing.assert_allclose(patch_pos.numpy(), want[0, 1:].numpy(), atol=1e-6)
+    np.testing.assert_allclose(cls_pos.numpy(), want[0, 0].numpy(), atol=0)
+    same_cls, same = benc.interpolate_pos_embed(sd["embeddings.position_embeddings"], 37, 37)
+    assert torch.equal(same, sd["embeddings.position_embeddings"][0, 1:])
+
+
 def test_preprocess_processor_matches_hf_processor():
     from transformers import DINOv3ViTImageProcessor
     frames = oenc.synthetic_frames(2, 96, 96, seed=3)
