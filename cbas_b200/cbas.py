@@ -23,6 +23,9 @@ from .classifier_head import ClassifierLSTMDeltas, actogram_bins
 from .encoder import DinoEncoder
 
 CHUNK_SIZE = 512  # cbas.py:48
+# worker processes that decode chunks ahead of encode_file (cbas_b200/decode.py); 0 = decode in the calling thread
+# exactly like the reference.  Set from the environment or by assigning cbas.DECODE_WORKERS.
+DECODE_WORKERS = int(os.environ.get("CBAS_B200_DECODE_WORKERS", "0"))
 
 
 # ----------------------------------------------------------------------------------------------- video decode
@@ -107,7 +110,12 @@ def encode_file(encoder, path: str, progress_callback: Optional[Callable[[float]
     receives the percentage after each 512-frame chunk has been decoded, from the calling thread."""
     if not isinstance(encoder, DinoEncoder):
         raise TypeError("cbas_b200.encode_file needs a cbas_b200.DinoEncoder (there is no PyTorch fallback path)")
-    reader = VideoReader(path)  # decoder errors propagate, as in the reference (cbas.py:400-402)
+    # decoder errors propagate, as in the reference (cbas.py:400-402)
+    if DECODE_WORKERS > 0 and not path.lower().endswith(".npy"):
+        from .decode import ParallelVideoReader
+        reader = ParallelVideoReader(path, workers=DECODE_WORKERS, chunk=CHUNK_SIZE)
+    else:
+        reader = VideoReader(path)
     video_len = len(reader)
     if video_len == 0:
         print(f"Warning: Video {path} contains no frames. Skipping.")

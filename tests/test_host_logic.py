@@ -114,6 +114,39 @@ def test_video_reader_decodes_mp4(tmp_path):
     r.close()
 
 
+def test_parallel_video_reader_matches_sequential_decode(tmp_path):
+    """Chunks decoded ahead by worker processes into shared memory are the frames the in-thread reader returns,
+    in order, including the short last chunk; out-of-order requests and broken files are reported."""
+    cv2 = pytest.importorskip("cv2")
+    from cbas_b200.decode import ParallelVideoReader
+    p = str(tmp_path / "v.mp4")
+    vw = cv2.VideoWriter(p, cv2.VideoWriter_fourcc(*"mp4v"), 30.0, (64, 48))
+    if not vw.isOpened():
+        pytest.skip("no mp4 encoder in this OpenCV build")
+    rng = np.random.default_rng(0)
+    base = rng.integers(0, 255, (48, 64, 3), dtype=np.uint8)
+    for i in range(141):
+        vw.write(np.roll(base, 3 * i, axis=1))
+    vw.release()
+    seq = cbas.VideoReader(p)
+    want = seq.get_batch(range(0, len(seq)))
+    seq.close()
+    par = ParallelVideoReader(p, workers=3, chunk=32)
+    try:
+        assert len(par) == 141 and par.n_chunks == 5
+        got = []
+        for i in range(0, 141, 32):
+            b = par.get_batch(range(i, min(i + 32, 141)))
+            got.append(np.array(b))  # copy: the view is recycled two requests later
+        assert np.array_equal(np.concatenate(got), want)
+        with pytest.raises(ValueError):
+            par.get_batch(range(0, 32))  # chunks are served once, in order
+    finally:
+        par.close()
+    with pytest.raises(FileNotFoundError):
+        ParallelVideoReader(str(tmp_path / "missing.mp4"))
+
+
 def test_infer_file_swallows_errors_and_returns_none(tmp_path, capsys):
     out = cbas.infer_file(str(tmp_path / "nope_cls.h5"), nn.Linear(1, 1), "m", ["a"], 31, device="cpu")
     assert out is None and "Error during buffered inference" in capsys.readouterr().out
