@@ -137,7 +137,7 @@ def run_reference(args, rank):
     fpst = 4
     fps, dt, threads, done = cpu_reference_fps(fpst, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC.replace("vitb16", args.arch), "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "DINOv3 ViT-B/16 224px streamed encode of a synthetic 10-min 30fps 256x256 clip "
@@ -417,7 +417,7 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC.replace("vitb16", args.arch), "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"DINOv3 {args.arch} {side}px streamed encode of a synthetic 10-min 30fps "
