@@ -17,7 +17,7 @@
 namespace cbas {
 
 constexpr int ATT_HEAD_DIM = 64;
-constexpr int ATT_THREADS = 128;
+constexpr int ATT_MAX_THREADS = 256;  // the launcher picks 4..8 warps so that the 16-row query tiles divide evenly
 constexpr int ATT_KEY_BLOCK = 64;
 
 __device__ __forceinline__ uint32_t att_swz(int row, int chunk) {
@@ -30,11 +30,16 @@ __device__ __forceinline__ void rope_pair(uint4& lo, uint4& hi, const float* __r
     // cos[i+32] == cos[i]).  out_lo = lo*cos - hi*sin ; out_hi = hi*cos + lo*sin
     uint32_t* l = reinterpret_cast<uint32_t*>(&lo);
     uint32_t* h = reinterpret_cast<uint32_t*>(&hi);
+    // 8 consecutive table entries each (32-byte aligned: the row pitch is 128 B and the offset 32*c B)
+    const float4 ca = __ldg(reinterpret_cast<const float4*>(cs)), cb = __ldg(reinterpret_cast<const float4*>(cs) + 1);
+    const float4 sa = __ldg(reinterpret_cast<const float4*>(sn)), sb = __ldg(reinterpret_cast<const float4*>(sn) + 1);
+    const float cc[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+    const float ss[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float2 a = unpack_bf16(l[i]), b = unpack_bf16(h[i]);
-        const float c0 = __ldg(cs + 2 * i), c1 = __ldg(cs + 2 * i + 1);
-        const float s0 = __ldg(sn + 2 * i), s1 = __ldg(sn + 2 * i + 1);
+        const float c0 = cc[2 * i], c1 = cc[2 * i + 1];
+        const float s0 = ss[2 * i], s1 = ss[2 * i + 1];
         l[i] = pack_bf16(a.x * c0 - b.x * s0, a.y * c1 - b.y * s1);
         h[i] = pack_bf16(b.x * c0 + a.x * s0, b.y * c1 + a.y * s1);
     }
@@ -79,7 +84,7 @@ __device__ __forceinline__ void att_key_block(const uint32_t (&qf)[4][4], uint32
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
         const float mn = fmaxf(m[r], mx[r]);
-        alpha[r] = exp2f(m[r] - mn);  // m = -inf on the first block -> 0
+        alpha[r] = ex2_approx(m[r] - mn);  // m = -inf on the first block -> 0
         m[r] = mn;
     }
     float rs[2] = {0.f, 0.f};
@@ -87,7 +92,7 @@ __device__ __forceinline__ void att_key_block(const uint32_t (&qf)[4][4], uint32
     for (int j = 0; j < NT; ++j) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            s[j][e] = exp2f(s[j][e] - m[e >> 1]);
+            s[j][e] = ex2_approx(s[j][e] - m[e >> 1]);  // one MUFU; masked keys are -inf -> 0
             rs[e >> 1] += s[j][e];
         }
     }
@@ -119,8 +124,8 @@ __device__ __forceinline__ void att_key_block(const uint32_t (&qf)[4][4], uint32
 }
 
 // qkv: [frames*T, 3*D] bf16 (q | k | v, head h at column h*64 of each third);  out: [frames*T, D] bf16.
-// rope_cos / rope_sin: [T - prefix, 32] fp32.   grid = frames * heads, block = 128, dyn smem = 3*TP*128 B.
-__global__ void __launch_bounds__(ATT_THREADS)
+// rope_cos / rope_sin: [T - prefix, 32] fp32.   grid = frames * heads, block = 128..256, dyn smem = 3*TP*128 B.
+__global__ void __launch_bounds__(ATT_MAX_THREADS)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                  const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int T, int prefix,
                  int heads, int D, float scale_log2) {
@@ -135,7 +140,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     const __nv_bfloat16* base = qkv + (long long)frame * T * ld + head * ATT_HEAD_DIM;
 
     // ---- prologue: gather + RoPE
-    for (int idx = tid; idx < TP * 4; idx += ATT_THREADS) {
+    for (int idx = tid; idx < TP * 4; idx += blockDim.x) {
         const int row = idx >> 2, c = idx & 3;
         uint4 qlo = make_uint4(0, 0, 0, 0), qhi = qlo, klo = qlo, khi = qlo, vlo = qlo, vhi = qlo;
         if (row < T) {
@@ -167,7 +172,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     const int full_blocks = TP / ATT_KEY_BLOCK;
     const int tail_tiles = (TP % ATT_KEY_BLOCK) >> 3;
 
-    for (int mt = warp; mt < m_tiles; mt += ATT_THREADS / 32) {
+    for (int mt = warp; mt < m_tiles; mt += (blockDim.x >> 5)) {
         uint32_t qf[4][4];
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {

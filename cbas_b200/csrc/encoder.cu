@@ -72,8 +72,16 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* 
     }
     const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
     if (!cs || !sn) prefix = T;  // no rotary embedding (DINOv2): no token is a "patch token" for the rotation
-    attention_kernel<<<frames * heads, ATT_THREADS, smem, s>>>(qkv, out, cs, sn, T, prefix, heads, heads * ATT_HEAD_DIM,
-                                                               scale_log2);
+    // warps per CTA: the one in 4..8 that wastes the fewest 16-row query-tile slots (ties: more warps hide more latency)
+    const int m_tiles = TP / 16;
+    int warps = 4;
+    double best = 0.0;
+    for (int w = 4; w <= ATT_MAX_THREADS / 32; ++w) {
+        const double eff = (double)m_tiles / (double)(((m_tiles + w - 1) / w) * w);
+        if (eff >= best) { best = eff; warps = w; }
+    }
+    attention_kernel<<<frames * heads, warps * 32, smem, s>>>(qkv, out, cs, sn, T, prefix, heads, heads * ATT_HEAD_DIM,
+                                                            scale_log2);
     count_launch();
     return check_cuda(cudaGetLastError(), "attention_kernel launch");
 }
