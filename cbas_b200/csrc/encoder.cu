@@ -5,6 +5,7 @@
 #include "../../include/cbas_b200.h"
 #include "attention.cuh"
 #include "attention_tc.cuh"
+#include "attention_tc_split.cuh"
 #include "common.h"
 #include "gemm_tcgen05.cuh"
 #include "layernorm.cuh"
@@ -96,8 +97,15 @@ bool attention_tc_fits(int T, int prefix) {
     const int TK = (T + 15) & ~15;
     return TK <= 256 && atc_smem_bytes(TK, T, prefix, true) <= 232448;
 }
-bool use_attention_tc(int T, int prefix) {
-    return g_attention_impl >= 2 || (g_attention_impl == 0 && attention_tc_fits(T, prefix));
+// 257..384 tokens: the key-split tcgen05 kernel (attention_tc_split.cuh)
+bool attention_tc_split_fits(int T, int prefix, bool rope) {
+    const int TK = (T + 15) & ~15;
+    return TK > 256 && TK <= 384 && ats_smem_bytes(TK, T, prefix, rope) <= 232448;
+}
+bool use_attention_tc(int T, int prefix, bool rope = true) {
+    if (g_attention_impl == 1) return false;
+    if (attention_tc_split_fits(T, prefix, rope)) return true;
+    return g_attention_impl >= 2 || attention_tc_fits(T, prefix);
 }
 
 // cs/sn: RoPE tables applied in the kernel's prologue, or null when q and k arrive rotated (EPI_QKV_ROPE_BF16)
@@ -105,7 +113,36 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const floa
                         int T, int prefix, int heads, cudaStream_t s) {
     if (frames <= 0) return 0;
     const int TK = (T + 15) & ~15;
-    if (TK > 256) return fail("tcgen05 attention handles at most 256 tokens per frame");
+    if (TK > 256) {
+        // key-split kernel for 257..384 tokens
+        const bool rope = cs != nullptr && sn != nullptr;
+        if (TK > 384 || !attention_tc_split_fits(T, prefix, rope))
+            return fail("tcgen05 attention handles at most 384 tokens per frame");
+        if (rope && (prefix < 0 || prefix >= T)) return fail("attention: bad prefix token count");
+        ProfScope prof(PROF_ATTENTION, s);
+        const int D = heads * 64;
+        const long long M = (long long)frames * T;
+        const int nq = (T + 127) / 128, TK0 = ats_key_block0(TK), TK1 = TK - TK0;
+        CUtensorMap tq, tk0, tk1, to, to1;
+        if (int rc = make_tmap_2d(&tq, qkv, false, (int)M, 3 * D, 3 * D, 64, 128)) return rc;
+        if (int rc = make_tmap_2d(&tk0, qkv, false, (int)M, 3 * D, 3 * D, 64, TK0)) return rc;
+        if (int rc = make_tmap_2d(&tk1, qkv, false, (int)M, 3 * D, 3 * D, 64, TK1)) return rc;
+        if (int rc = make_tmap_3d_bf16(&to, out, D, T, frames, D, 64, 128)) return rc;
+        if (int rc = make_tmap_3d_bf16(&to1, out, D, T, frames, D, 64, T - 128 * (nq - 1))) return rc;
+        const int smem = ats_smem_bytes(TK, T, prefix, rope);
+        static int configured_split = 0;
+        if (smem > configured_split) {
+            CBAS_CHECK(cudaFuncSetAttribute(attention_tc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured_split = smem;
+        }
+        AttnTcParams p{qkv, out, frames, heads, T, TK, D, 0.125f * 1.4426950408889634f, rope ? cs : nullptr,
+                       rope ? sn : nullptr, prefix, 0, nullptr};
+        const int items = frames * heads;
+        const int grid = items < sm_count() ? items : sm_count();
+        attention_tc_split_kernel<<<grid, ATC_THREADS, smem, s>>>(tq, tk0, tk1, to, to1, p);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "attention_tc_split_kernel launch");
+    }
     ProfScope prof(PROF_ATTENTION, s);
     const int D = heads * 64;
     const long long M = (long long)frames * T;
@@ -276,7 +313,7 @@ int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
                                                  c.ln_eps, s)) return rc;
     GemmParams p{};
     p.M = M; p.N = 3 * D; p.K = D; p.bias = (const float*)L.b_qkv; p.out = e->qkv; p.ldo = 3 * D;
-    if (use_attention_tc(e->T, c.prefix_tokens)) {
+    if (use_attention_tc(e->T, c.prefix_tokens, e->w.rope_cos != nullptr)) {
         // QKV projection (V stored as f16); the tcgen05 attention kernel rotates q and k in its prologue
         p.f16_from = 2 * D;
         if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16_VF16, s, PROF_QKV_GEMM))
@@ -309,7 +346,7 @@ int encoder_last_layer_cls_only(cbas_encoder* e, int li, int n, cudaStream_t s) 
     const cbas_encoder_cfg& c = e->cfg;
     const cbas_layer_weights& L = e->layers[li];
     const int D = c.hidden, I = c.intermediate, T = e->T, M = n * T;
-    const bool tc = use_attention_tc(T, c.prefix_tokens);
+    const bool tc = use_attention_tc(T, c.prefix_tokens, e->w.rope_cos != nullptr);
     if (int rc = launch_layernorm<__nv_bfloat16>(e->h, 1, (const float*)L.ln1_g, (const float*)L.ln1_b, e->xn, M, D,
                                                  c.ln_eps, s)) return rc;
     const __nv_bfloat16* wqkv = (const __nv_bfloat16*)L.w_qkv;

@@ -94,6 +94,28 @@ def test_attention_tcgen05_rope_prologue(side, heads, frames):
     assert rel_err(out, legacy) < 1.5e-2
 
 
+@pytest.mark.parametrize("T,heads,frames,rope_side", [(261, 12, 3, 16), (261, 12, 37, 16), (329, 12, 4, 0), (329, 6, 11, 18),
+                                                     (272, 16, 2, 0), (384, 12, 2, 0), (257, 12, 3, 0)])
+def test_attention_tcgen05_key_split(T, heads, frames, rope_side):
+    """257..384 tokens per frame (256-px frames; DINOv2-with-registers): the key-split kernel merges two partial
+    softmaxes per query tile; with and without the RoPE prologue, vs torch SDPA and vs the mma.sync kernel."""
+    P, D = 5, heads * 64
+    qkv, x = _qkv_with_f16_v(frames, T, D, heads)
+    if rope_side:
+        assert rope_side * rope_side + P == T
+        cos, sin = rope_tables(rope_side, rope_side)
+        cos, sin = cos.cuda(), sin.cuda()
+        out = attention_tc(qkv, frames, T, heads, cos, sin, P).float()
+        q, k = _rope_ref(x[0], x[1], cos, sin)
+    else:
+        out = attention_tc(qkv, frames, T, heads).float()
+        q, k = x[0], x[1]
+    want = F.scaled_dot_product_attention(q, k, x[2], scale=0.125).permute(0, 2, 1, 3).reshape(frames * T, D)
+    e = rel_err(out, want)
+    assert e < 1.5e-2, f"key-split tcgen05 attention rel err {e}"
+    assert torch.isfinite(out).all()
+
+
 def test_rope_tables_match_hf_module():
     from transformers import DINOv3ViTConfig
     from transformers.models.dinov3_vit.modeling_dinov3_vit import DINOv3ViTRopePositionEmbedding
