@@ -411,6 +411,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             }
             if (stamper) ATC_STAMP(sbase + 4);
         }
+        if ((warp & 7) == 0 && elect_one()) tma_wait_group<0>();  // this CTA's output stores have landed
     }
 
     __syncwarp();

@@ -8,9 +8,11 @@
 //   * pipeline p (its own MMA-issuing warp, eight softmax warps, TMEM columns [256p, 256p+256)) computes, for the
 //     current 128-row query tile, S_p = Q K_p^T, a softmax over ITS key block only (block max m_p, block sum l_p,
 //     probabilities relative to m_p) and O_p = P_p V_p;
-//   * the epilogue merges the two partial results exactly:  w_p = 2^(c (m_p - max(m_0, m_1))),
+//   * the partial results are merged exactly:  w_p = 2^(c (m_p - max(m_0, m_1))),
 //     O = (w_0 O_0 + w_1 O_1) / (w_0 l_0 + w_1 l_1)  - the standard split-K (flash-decoding) identity, so there
-//     is no running rescale of O inside the loop;
+//     is no running rescale of O inside the loop.  Pipeline 1 runs half a tile behind pipeline 0 and ITS warps do
+//     the merge, staging and store; pipeline 0 never waits for pipeline 1 (its O_0 simply stays in TMEM until the
+//     merge has read it), so one pipeline's MMAs and drain fall into the other's softmax;
 //   * the query tiles of a frame (three of them) run one after the other against the resident K and V.
 //
 // Shared memory holds ONE frame-head at a time (Q tiles + K + V, up to 134 KB) next to the output staging rows and
@@ -23,7 +25,7 @@
 
 namespace cbas {
 
-constexpr int ATS_XCHG_BYTES = (2 * 2 * 2 * 128 + 2 * 128) * 4;  // [max|sum][pipe][half][row] + block max [pipe][row]
+constexpr int ATS_XCHG_BYTES = (2 * 2 * 128 + 2 * 2 * 2 * 128 + 2 * 2 * 128) * 4;  // max [pipe][half][row]; per tile parity: sums [pipe][half][row], block max [pipe][row]
 
 __host__ __device__ inline int ats_key_block0(int TK) { return ((TK + 31) / 32) * 16; }
 __host__ __device__ inline int ats_smem_bytes(int TK, int T, int prefix, bool rope) {
@@ -51,7 +53,6 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
     uint8_t* ostage = v_s + TK * 128;             // [T][128 B] output rows of the current item
     __half2* rope_tab = reinterpret_cast<__half2*>(ostage + atc_stage_bytes(T));
     float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(rope_tab) + (rope ? atc_rope_bytes(T, p.prefix) : 0));
-    float* blockmax = xchg + 2 * 2 * 2 * 128;     // [pipe][row]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + ATS_XCHG_BYTES);
     uint64_t* qk_full = bars;        // TMA -> rotation warps (or MMA): Q tiles + K landed
     uint64_t* qk_empty = bars + 1;   // both MMA warps -> TMA: the item's last S MMAs retired
@@ -61,7 +62,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
     uint64_t* s_full = bars + 5;     // [2] per pipeline: MMA -> softmax
     uint64_t* p_full = bars + 7;     // [2] softmax -> MMA
     uint64_t* o_full = bars + 9;     // [2] MMA -> epilogue
-    uint64_t* o_empty = bars + 11;   // [2] epilogue (all 16 warps read both partial outputs) -> MMA
+    uint64_t* o_empty = bars + 11;   // [2] merge (the 8 warps of pipeline 1 read both partial outputs) -> MMA
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,7 +85,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 8);
             mbar_init(&o_full[i], 1);
-            mbar_init(&o_empty[i], ATC_SOFTMAX_WARPS);
+            mbar_init(&o_empty[i], 8);
         }
         fence_mbar_init();
     }
@@ -136,12 +137,14 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
         const uint32_t q_u = smem_u32(q_s);
         const uint64_t dk = umma_desc_sw128(smem_u32(k_s) + pp * TK0 * 128);
         const uint64_t dv = umma_desc_sw128_mn(smem_u32(v_s) + pp * TK0 * 128);
-        // (no stagger between the pipelines here: the merge needs both partial results of a tile at the same time)
+        if (pp == 1) mbar_wait(&p_full[0], 0);  // half a tile late: the two pipelines' MMA and softmax phases interleave
         int it = 0, g = 0;
         for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
             mbar_wait(rope ? qk_ready : qk_full, it & 1);
             for (int qt = 0; qt < nq; ++qt, ++g) {
-                mbar_wait(&o_empty[pp], (g & 1) ^ 1);  // the previous tile's partial O (inside this S region) was drained
+                // S overwrites the previous tile's P (same columns): that tile's PV must have retired.  O sits at
+                // +192..+256, beyond any S of this kernel (TKp <= 192), so S does not wait for the merge.
+                if (g > 0) mbar_wait(&o_full[pp], (g - 1) & 1);
                 tc_fence_after();
                 const uint64_t dq = umma_desc_sw128(q_u + qt * 16384);
                 if (elect_one()) {
@@ -153,6 +156,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
                 __syncwarp();
                 if (qt == 0) mbar_wait(v_full, it & 1);
                 mbar_wait(&p_full[pp], g & 1);
+                mbar_wait(&o_empty[pp], (g & 1) ^ 1);  // the merge has read the previous tile's partial O
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
@@ -203,14 +207,16 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
         const int c_begin = half ? CA : 0, c_end = half ? TKp : CA;
         float* my_max = xchg + ((0 * 2 + pp) * 2 + half) * 128 + rit;
         float* peer_max = xchg + ((0 * 2 + pp) * 2 + (half ^ 1)) * 128 + rit;
-        float* sums = xchg + 1 * 2 * 2 * 128;  // [pipe][half][row]
-        const int ocol = 16 * (2 * pp + half);  // the 16 output columns this thread merges and stores
+        float* sums_all = xchg + 2 * 2 * 128;                  // [tile parity][pipe][half][row]
+        float* bmax_all = xchg + 2 * 2 * 128 + 2 * 2 * 2 * 128;  // [tile parity][pipe][row]
         int it = 0, g = 0;
         for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
             const int f = w / p.heads, h = w % p.heads;
             for (int qt = 0; qt < nq; ++qt, ++g) {
                 const int row = qt * 128 + rit;
                 const bool warp_has_rows = (qt * 128 + quarter * 32) < T;
+                float* sums = sums_all + (g & 1) * 512;
+                float* blockmax = bmax_all + (g & 1) * 256;
                 mbar_wait(&s_full[pp], g & 1);
                 tc_fence_after();
                 float sum = 0.f;
@@ -273,25 +279,38 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[pp]);
 
-                // ---- merge the two key blocks: this thread owns 16 output columns of its row
+                if (pp == 0) continue;  // pipeline 0 goes straight on to the next tile
+
+                // ---- merge (pipeline 1 only): this thread owns 32 output columns of its row, 16 at a time
                 mbar_wait(&o_full[0], g & 1);
                 mbar_wait(&o_full[1], g & 1);
                 tc_fence_after();
-                uint32_t o0[16], o1[16];
-                float w0 = 0.f, w1 = 0.f, inv = 0.f;
+                float w0 = 0.f, w1 = 0.f;
+                uint32_t packed[16];
                 if (warp_has_rows) {
-                    tmem_ld_32x16(t_lane + ATC_O_COL + ocol, o0);
-                    tmem_ld_32x16(t_lane + 256 + ATC_O_COL + ocol, o1);
-                    tmem_ld_wait();
                     const float m0 = blockmax[rit], m1 = blockmax[128 + rit];
                     const float mm = fmaxf(m0, m1);
                     w0 = ex2_approx((m0 - mm) * c);
                     w1 = ex2_approx((m1 - mm) * c);
                     const float l0 = sums[rit] + sums[128 + rit], l1 = sums[256 + rit] + sums[384 + rit];
-                    inv = 1.0f / fmaf(w0, l0, w1 * l1);
+                    const float inv = 1.0f / fmaf(w0, l0, w1 * l1);
+                    w0 *= inv;
+                    w1 *= inv;
+#pragma unroll
+                    for (int part = 0; part < 2; ++part) {
+                        uint32_t o0[16], o1[16];
+                        tmem_ld_32x16(t_lane + ATC_O_COL + 32 * half + 16 * part, o0);
+                        tmem_ld_32x16(t_lane + 256 + ATC_O_COL + 32 * half + 16 * part, o1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2)
+                            packed[8 * part + (j >> 1)] =
+                                pack_bf16(fmaf(__uint_as_float(o0[j]), w0, __uint_as_float(o1[j]) * w1),
+                                          fmaf(__uint_as_float(o0[j + 1]), w0, __uint_as_float(o1[j + 1]) * w1));
+                    }
                 }
-                // everything this thread needs from TMEM and from the exchange arrays is in registers: both score
-                // regions may be overwritten by the next tile's S
+                // both partial outputs and the exchange rows of this tile are consumed: the next PV of either
+                // pipeline may overwrite its O columns
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -299,28 +318,17 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
                     mbar_arrive(&o_empty[1]);
                 }
                 if (warp_has_rows && row < T) {
-                    w0 *= inv;
-                    w1 *= inv;
                     uint8_t* srow = ostage + row * 128;
 #pragma unroll
-                    for (int j = 0; j < 16; j += 8) {
-                        uint4 q;
-                        q.x = pack_bf16(fmaf(__uint_as_float(o0[j]), w0, __uint_as_float(o1[j]) * w1),
-                                        fmaf(__uint_as_float(o0[j + 1]), w0, __uint_as_float(o1[j + 1]) * w1));
-                        q.y = pack_bf16(fmaf(__uint_as_float(o0[j + 2]), w0, __uint_as_float(o1[j + 2]) * w1),
-                                        fmaf(__uint_as_float(o0[j + 3]), w0, __uint_as_float(o1[j + 3]) * w1));
-                        q.z = pack_bf16(fmaf(__uint_as_float(o0[j + 4]), w0, __uint_as_float(o1[j + 4]) * w1),
-                                        fmaf(__uint_as_float(o0[j + 5]), w0, __uint_as_float(o1[j + 5]) * w1));
-                        q.w = pack_bf16(fmaf(__uint_as_float(o0[j + 6]), w0, __uint_as_float(o1[j + 6]) * w1),
-                                        fmaf(__uint_as_float(o0[j + 7]), w0, __uint_as_float(o1[j + 7]) * w1));
-                        *reinterpret_cast<uint4*>(srow + ((((ocol >> 3) + (j >> 3)) ^ (rit & 7)) << 4)) = q;
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(srow + (((4 * half + j) ^ (rit & 7)) << 4)) =
+                            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                 }
                 // one TMA store per query tile; the staging rows of tile qt are rewritten one item later, after this
-                // thread has passed the next barrier below, i.e. after the wait on the store's shared-memory read
+                // thread has passed the barrier again, i.e. after the wait on the store's shared-memory read
                 fence_proxy_async();
-                named_bar_sync(3, 512);
-                if (warp == 0) {
+                named_bar_sync(3, 256);
+                if (warp == 8) {
                     if (elect_one()) {
                         if (qt == nq - 1) tma_store_3d(&tmap_o1, ostage + qt * 16384, h * 64, qt * 128, f);
                         else tma_store_3d(&tmap_o, ostage + qt * 16384, h * 64, qt * 128, f);
@@ -331,6 +339,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
                 }
             }
         }
+        if (warp == 8 && elect_one()) tma_wait_group<0>();  // this CTA's output stores have landed
     }
 
     __syncwarp();
