@@ -270,7 +270,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                     if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_F32) {
 #pragma unroll
-                        for (int j = 0; j < kHalf; ++j) x[j] = gelu_erf_fast(x[j]);
+                        for (int j = 0; j < kHalf; ++j) x[j] = gelu_erf_fast<EPI == EPI_BIAS_GELU_BF16 ? 3 : 5>(x[j]);
                     }
                     // the bulk store issued from THIS slab buffer two slabs ago must have finished reading it
                     uint8_t* slab = group_slabs + sbuf * GEMM_SLAB_BYTES;

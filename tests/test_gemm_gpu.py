@@ -51,7 +51,7 @@ def test_gemm_gelu_f32():
     a, w, b = _mk(1029, 256, 1152, seed=4)
     out = gemm(a, w, b, epi=5)
     want = torch.nn.functional.gelu(a.float() @ w.float().T + b)
-    assert rel_err(out, want) < 3e-5  # epilogue GELU: |error| <= 8.6e-6 absolute (see gelu_erf_fast)
+    assert rel_err(out, want) < 5e-6  # fp32 epilogue GELU: |error| <= 5.1e-7 absolute (gelu_erf_fast<5>)
 
 
 def test_gemm_residual_inplace():

@@ -8,7 +8,7 @@ import json,sys
 for l in sys.stdin:
     j=json.loads(l)
     if 'kernels_ms' in j: print('${lib:-current}'.split('/')[-1][-28:], j['tokens'], round(j['frames_per_s']), j['kernels_ms']['attention'])
-    else: print('${lib:-current}'.split('/')[-1][-28:], round(j['value']), round(j['ms_per_step'],3), j['clocks']['sm_mhz'], round(j['forward']['kernels']['attention']['ms_per_step'],3))
+    else: print('${lib:-current}'.split('/')[-1][-28:], round(j['value']), round(j['ms_per_step'],3), j['clocks']['sm_mhz'], ' '.join(k[:4]+'='+str(round(v['ms_per_step'],2)) for k,v in j['forward']['kernels'].items()))
 "
   done
 done
