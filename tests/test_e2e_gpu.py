@@ -62,6 +62,36 @@ def test_encode_infer_actogram_chain(tmp_path, monkeypatch):
     assert act2.binned_activity == act.binned_activity
 
 
+def test_encode_file_from_mp4_with_parallel_decode(tmp_path, monkeypatch):
+    """A real container file through encode_file: the in-thread decoder (the reference's arrangement) and the
+    process-pool decoder must produce the same `_cls.h5`, and both must match the oracle run on the decoded frames."""
+    cv2 = pytest.importorskip("cv2")
+    clip = str(tmp_path / "cam2_00001.mp4")
+    vw = cv2.VideoWriter(clip, cv2.VideoWriter_fourcc(*"mp4v"), 10.0, (64, 64))
+    if not vw.isOpened():
+        pytest.skip("no mp4 encoder in this OpenCV build")
+    for f in oenc.synthetic_frames(75, 64, 64, seed=21):
+        vw.write(f[:, :, ::-1].copy())  # RGB -> BGR
+    vw.release()
+    monkeypatch.setattr(gui_state, "proj", None)
+    monkeypatch.setattr(cbas, "CHUNK_SIZE", 32)
+    enc = DinoEncoder("synthetic:vits16@3", "cuda", max_frames=32)
+    outs = {}
+    for workers in (0, 3):
+        monkeypatch.setattr(cbas, "DECODE_WORKERS", workers)
+        out = cbas.encode_file(enc, clip)
+        with store.EmbeddingReader(out) as r:
+            assert r.shape == (75, 384)
+            outs[workers] = r.read(0, 75)
+        os.remove(out)
+    assert np.array_equal(outs[0], outs[3])  # same frames, same kernels -> identical f16 rows
+    reader = cbas.VideoReader(clip)
+    decoded = reader.get_batch(range(75))
+    reader.close()
+    direct = enc.encode_u8(torch.from_numpy(decoded).cuda()).cpu().numpy().astype(np.float16)
+    assert np.abs(outs[0].astype(np.float32) - direct.astype(np.float32)).max() <= 2e-3 * np.abs(direct.astype(np.float32)).max()
+
+
 def test_worker_threads_encode_then_classify(tmp_path, monkeypatch):
     frames = oenc.synthetic_frames(40, 64, 64, seed=12)
     clips = []
