@@ -4,6 +4,7 @@
 // (modeling_dinov3_vit.py:530-555).  Residual stream is fp32; GEMM operands are bf16 with fp32 accumulation.
 #include "../../include/cbas_b200.h"
 #include "attention.cuh"
+#include <algorithm>
 #include "attention_tc.cuh"
 #include "attention_tc_split.cuh"
 #include "common.h"
@@ -88,7 +89,7 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* 
 }
 
 bool g_prune_last_layer = true;  // false: run the last block on every token (test knob)
-bool g_resize_tiled = true;  // false: per-pixel kernel (test knob)
+int g_resize_tiled = 2;  // test knob: 0 per-pixel kernel, 1 general tiled kernel, 2 column-per-thread kernel when it applies
 long long* g_attention_trace = nullptr;  // device buffer [64][ATC_TRACE_SLOTS] for the stage-timing aid (tools/attn_trace.py)
 int g_attention_dbg = 0;  // AttnTcParams::dbg (timing experiments)
 int g_attention_impl = 0;  // 0 auto (tcgen05 when T <= 256), 1 mma.sync, 2 tcgen05 (both rotate q,k in their prologue)
@@ -197,8 +198,25 @@ int launch_preprocess_resize(const uint8_t* frames, __nv_bfloat16* A, int n, int
     const int max_rows = (int)((16LL * H + side - 1) / side) + tp.taps_y + 1;
     const int src_pitch = (W * 3 + 15) & ~15;
     const size_t tile_smem = (size_t)max_rows * src_pitch + (size_t)max_rows * side * 3 * 4;
-    if (g_resize_tiled && tile_smem <= 200 * 1024 && (reinterpret_cast<uintptr_t>(frames) & 15) == 0 && fs % 16 == 0 &&
-        rs % 16 == 0) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(frames) & 15) == 0 && fs % 16 == 0 && rs % 16 == 0;
+    if (g_resize_tiled >= 2 && aligned && side <= 256 && tp.taps_x <= RESIZE_FAST_TAPS && tp.taps_y <= RESIZE_FAST_TAPS) {
+        // production path: column-per-thread kernel (bitwise identical to the general tiled kernel below)
+        const int io_bytes = std::max(max_rows * src_pitch, (side / 16) * 1536);
+        const size_t smem = (size_t)io_bytes + (size_t)3 * max_rows * side * 4 + 16 * 32 + 32;  // + row taps, + slack for the word-wise reads of the last staged row
+        if (smem <= 110 * 1024) {
+            static size_t configured_fast = 0;
+            if (smem > configured_fast) {
+                CBAS_CHECK(cudaFuncSetAttribute(preprocess_resize_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem));
+                configured_fast = smem;
+            }
+            preprocess_resize_fast_kernel<<<n * (side / 16), 256, smem, s>>>(frames, A, H, W, fs, rs, side, tp, mean, istd,
+                                                                            max_rows, io_bytes);
+            count_launch();
+            return check_cuda(cudaGetLastError(), "preprocess_resize_fast_kernel launch");
+        }
+    }
+    if (g_resize_tiled && tile_smem <= 200 * 1024 && aligned) {
         static size_t configured = 0;
         if (tile_smem > configured) {
             CBAS_CHECK(cudaFuncSetAttribute(preprocess_resize_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -524,7 +542,7 @@ int cbas_b200_debug_prune_last_layer(int32_t on) {
 }
 
 int cbas_b200_debug_resize_tiled(int32_t on) {
-    g_resize_tiled = on != 0;
+    g_resize_tiled = on < 0 ? 0 : (on > 2 ? 2 : on);  // 0 per-pixel, 1 general tiled, 2 column-per-thread (default)
     return 0;
 }
 

@@ -212,6 +212,119 @@ preprocess_resize_tile_kernel(const uint8_t* __restrict__ frames, __nv_bfloat16*
     }
 }
 
+// Production version of the tiled resize for the benchmark geometry (S <= 256 output columns, <= 5 taps per axis:
+// 256 -> 224 has 5).  Same arithmetic, in the same order, as preprocess_resize_tile_kernel - the two are bitwise
+// identical - but shaped for instruction-level parallelism instead of generality: one thread per output COLUMN keeps
+// its horizontal taps and byte offsets in registers and walks the staged rows (no index division, no tap loads in the
+// loop); the row taps of the 16 output rows sit in shared memory; the finished patch-matrix rows of this patch row
+// (ns x 768 bf16, contiguous in global memory) are assembled in shared memory and leave with 16-byte coalesced stores.
+constexpr int RESIZE_FAST_TAPS = 5;
+
+__global__ void __launch_bounds__(256)
+preprocess_resize_fast_kernel(const uint8_t* __restrict__ frames, __nv_bfloat16* __restrict__ A, int H, int W,
+                              long long frame_stride, int row_stride, int S, ResizeTaps tp, float3 mean,
+                              float3 inv_std, int max_rows, int io_bytes) {
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    const int ns = S >> 4;
+    const int f = blockIdx.x / ns, py = blockIdx.x % ns;
+    const int y_first = py * 16;
+    const int r0 = __ldg(tp.ymin + y_first);
+    int r1 = __ldg(tp.ymin + y_first + 15) + tp.taps_y;
+    r1 = r1 < H ? r1 : H;
+    const int nrows = r1 - r0;
+    const int row_bytes = W * 3;
+    const int src_pitch = (row_bytes + 15) & ~15;
+    uint8_t* src = rs_smem;                                                   // [max_rows][src_pitch], later out_s
+    float* hbuf = reinterpret_cast<float*>(rs_smem + io_bytes);               // [3][max_rows][S]
+    float4* ytab = reinterpret_cast<float4*>(hbuf + 3 * max_rows * S);        // [16][2]: w0..w3 | w4, first row, -, -
+    const int t = threadIdx.x;
+    const uint8_t* img = frames + f * frame_stride + (long long)r0 * row_stride;
+    // A: stage the source rows; the row taps of the 16 output rows
+    const int vec_per_row = src_pitch >> 4;
+    for (int i = t; i < nrows * vec_per_row; i += 256) {
+        const int r = i / vec_per_row, v = i - r * vec_per_row;
+        const uint8_t* g = img + (long long)r * row_stride + v * 16;
+        uint4 q;
+        if (v * 16 + 16 <= row_bytes) q = __ldg(reinterpret_cast<const uint4*>(g));
+        else {
+            uint8_t tmp[16];
+#pragma unroll
+            for (int b = 0; b < 16; ++b) tmp[b] = (v * 16 + b < row_bytes) ? g[b] : 0;
+            q = *reinterpret_cast<uint4*>(tmp);
+        }
+        *reinterpret_cast<uint4*>(src + r * src_pitch + v * 16) = q;
+    }
+    if (t < 16) {
+        float w[RESIZE_FAST_TAPS];
+#pragma unroll
+        for (int j = 0; j < RESIZE_FAST_TAPS; ++j)
+            w[j] = j < tp.taps_y ? __ldg(tp.wy + (y_first + t) * tp.taps_y + j) : 0.f;
+        ytab[2 * t] = make_float4(w[0], w[1], w[2], w[3]);
+        ytab[2 * t + 1] = make_float4(w[4], __int_as_float(__ldg(tp.ymin + y_first + t) - r0), 0.f, 0.f);
+    }
+    __syncthreads();
+    // B: horizontal pass, one output column per thread
+    if (t < S) {
+        float w[RESIZE_FAST_TAPS];
+        const int x0 = __ldg(tp.xmin + t);
+#pragma unroll
+        for (int k = 0; k < RESIZE_FAST_TAPS; ++k) w[k] = k < tp.taps_x ? __ldg(tp.wx + t * tp.taps_x + k) : 0.f;
+        // the 5 taps x 3 channels are 15 consecutive bytes from 3*x0 (taps past the right edge have weight 0, so what
+        // lies there - the row padding or the next staged row - does not matter): five aligned words, funnel-shifted
+        // into place, instead of fifteen byte loads (the kernel is bound by shared-memory instructions)
+        const int b0 = 3 * x0;
+        const int sh = (b0 & 3) * 8;
+        const uint8_t* base = src + (b0 & ~3);
+#pragma unroll 4
+        for (int r = 0; r < nrows; ++r) {
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(base + r * src_pitch);
+            const uint32_t q0 = wp[0], q1 = wp[1], q2 = wp[2], q3 = wp[3], q4 = wp[4];
+            const uint32_t a0 = __funnelshift_r(q0, q1, sh), a1 = __funnelshift_r(q1, q2, sh);
+            const uint32_t a2 = __funnelshift_r(q2, q3, sh), a3 = __funnelshift_r(q3, q4, sh);
+            // byte i of the 15-byte run = pixel i/3, channel i%3
+            float cr = 0.f, cg = 0.f, cb = 0.f;
+            cr += w[0] * float(a0 & 0xff);         cg += w[0] * float((a0 >> 8) & 0xff);  cb += w[0] * float((a0 >> 16) & 0xff);
+            cr += w[1] * float(a0 >> 24);          cg += w[1] * float(a1 & 0xff);         cb += w[1] * float((a1 >> 8) & 0xff);
+            cr += w[2] * float((a1 >> 16) & 0xff); cg += w[2] * float(a1 >> 24);          cb += w[2] * float(a2 & 0xff);
+            cr += w[3] * float((a2 >> 8) & 0xff);  cg += w[3] * float((a2 >> 16) & 0xff); cb += w[3] * float(a2 >> 24);
+            cr += w[4] * float(a3 & 0xff);         cg += w[4] * float((a3 >> 8) & 0xff);  cb += w[4] * float((a3 >> 16) & 0xff);
+            hbuf[(0 * max_rows + r) * S + t] = cr;
+            hbuf[(1 * max_rows + r) * S + t] = cg;
+            hbuf[(2 * max_rows + r) * S + t] = cb;
+        }
+    }
+    __syncthreads();
+    // C: vertical pass, normalise, assemble the patch-matrix rows in shared memory (over the dead source rows)
+    __nv_bfloat16* out_s = reinterpret_cast<__nv_bfloat16*>(src);  // [ns][768]
+    if (t < S) {
+        const float mu[3] = {mean.x, mean.y, mean.z}, is[3] = {inv_std.x, inv_std.y, inv_std.z};
+        __nv_bfloat16* o = out_s + (t >> 4) * 768 + (t & 15);
+        const float* hx = hbuf + t;
+        const int plane = max_rows * S;
+#pragma unroll 2
+        for (int ky = 0; ky < 16; ++ky) {
+            const float4 wa = ytab[2 * ky], wb = ytab[2 * ky + 1];
+            const int yo = __float_as_int(wb.y);
+            const float wy[RESIZE_FAST_TAPS] = {wa.x, wa.y, wa.z, wa.w, wb.x};
+            int rr[RESIZE_FAST_TAPS];
+#pragma unroll
+            for (int j = 0; j < RESIZE_FAST_TAPS; ++j) rr[j] = min(yo + j, nrows - 1) * S;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < RESIZE_FAST_TAPS; ++j) acc += wy[j] * hx[c * plane + rr[j]];
+                o[c * 256 + ky * 16] = __float2bfloat16_rn((acc * (1.0f / 255.0f) - mu[c]) * is[c]);
+            }
+        }
+    }
+    __syncthreads();
+    // D: ns consecutive rows of A are one contiguous block
+    uint4* dst = reinterpret_cast<uint4*>(A + ((long long)f * ns * ns + (long long)py * ns) * 768);
+    const uint4* so = reinterpret_cast<const uint4*>(out_s);
+    for (int i = t; i < ns * 96; i += 256) dst[i] = so[i];
+}
+
 // CLS + register rows of the residual stream (HF modeling_dinov3_vit.py:86-90): h[frame*T + j] = prefix[j], j < P
 __global__ void __launch_bounds__(256)
 fill_prefix_kernel(float* __restrict__ h, const float* __restrict__ prefix_tokens, int n_frames, int T, int P, int D) {

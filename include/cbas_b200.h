@@ -112,7 +112,8 @@ int cbas_b200_debug_attention_experiment(int mode);
 /* Test knob: 1 (default) = in the last block compute only what the pooled CLS row needs (K/V for all tokens, the
  * rest for the CLS rows), 0 = run the last block on every token.  Same result for the row that is kept. */
 int cbas_b200_debug_prune_last_layer(int32_t on);
-/* Test knob: 1 (default) = shared-memory tiled resize kernel when the geometry allows, 0 = per-pixel kernel. */
+/* Test knob: 2 (default) = column-per-thread resize kernel when the geometry allows (<= 256 output columns, <= 5 taps),
+ * 1 = general shared-memory tiled kernel, 0 = per-pixel kernel.  All three agree (1 and 2 bitwise). */
 int cbas_b200_debug_resize_tiled(int32_t on);
 /* Test knob: 0 = choose automatically (CTA pairs / tcgen05 cta_group::2 when M >= 4096), 1 or 2 = force. */
 int cbas_b200_debug_gemm_cta_group(int32_t cg);

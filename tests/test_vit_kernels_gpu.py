@@ -138,7 +138,7 @@ def test_preprocess_green_exact():
     assert torch.equal(A.float().cpu(), want)  # bytes are exact in bf16
 
 
-@pytest.mark.parametrize("tiled", [1, 0], ids=["tiled", "per_pixel"])
+@pytest.mark.parametrize("tiled", [2, 1, 0], ids=["column_per_thread", "tiled", "per_pixel"])
 @pytest.mark.parametrize("H,W,S", [(256, 256, 224), (96, 128, 64), (224, 224, 224), (48, 48, 64), (480, 640, 224)])
 def test_preprocess_resize_matches_oracle(H, W, S, tiled):
     _lib.check(_lib.lib().cbas_b200_debug_resize_tiled(tiled), "knob")
@@ -155,7 +155,14 @@ def test_preprocess_resize_matches_oracle(H, W, S, tiled):
     _lib.check(_lib.lib().cbas_b200_preprocess_resize(
         f.data_ptr(), A.data_ptr(), 2, H, W, H * W * 3, W * 3, S, ymin_d.data_ptr(), wy_d.data_ptr(), wy.shape[1],
         xmin_d.data_ptr(), wx_d.data_ptr(), wx.shape[1], stream()), "resize")
-    _lib.lib().cbas_b200_debug_resize_tiled(1)
+    if tiled == 2:  # the production kernel does the same arithmetic in the same order as the general tiled one
+        B = torch.empty_like(A)
+        _lib.lib().cbas_b200_debug_resize_tiled(1)
+        _lib.check(_lib.lib().cbas_b200_preprocess_resize(
+            f.data_ptr(), B.data_ptr(), 2, H, W, H * W * 3, W * 3, S, ymin_d.data_ptr(), wy_d.data_ptr(), wy.shape[1],
+            xmin_d.data_ptr(), wx_d.data_ptr(), wx.shape[1], stream()), "resize")
+        assert torch.equal(A, B)
+    _lib.lib().cbas_b200_debug_resize_tiled(2)
     got = A.float().cpu()
     # <= 1 bf16 ulp: |x| <= 2.7 -> ulp 2^-7 at most
     err = (got - want).abs()
