@@ -5,6 +5,7 @@
 #include "../../include/cbas_b200.h"
 #include "attention.cuh"
 #include <algorithm>
+#include <atomic>
 #include "attention_tc.cuh"
 #include "attention_tc_split.cuh"
 #include "common.h"
@@ -67,7 +68,7 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* 
     ProfScope prof(PROF_ATTENTION, s);
     const int TP = (T + 15) & ~15;
     const int smem = 3 * TP * 128;
-    static int configured_smem = 0;
+    static std::atomic<int> configured_smem{0};  // two host threads may race here: the attribute call is idempotent
     if (smem > configured_smem) {
         CBAS_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured_smem = smem;
@@ -131,7 +132,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const floa
         if (int rc = make_tmap_3d_bf16(&to, out, D, T, frames, D, 64, 128)) return rc;
         if (int rc = make_tmap_3d_bf16(&to1, out, D, T, frames, D, 64, T - 128 * (nq - 1))) return rc;
         const int smem = ats_smem_bytes(TK, T, prefix, rope);
-        static int configured_split = 0;
+        static std::atomic<int> configured_split{0};
         if (smem > configured_split) {
             CBAS_CHECK(cudaFuncSetAttribute(attention_tc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             configured_split = smem;
@@ -159,7 +160,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const floa
     if (rope && (prefix < 0 || prefix >= T)) return fail("attention: bad prefix token count");
     const int smem = atc_smem_bytes(TK, T, prefix, rope);
     if (smem > 232448) return fail("attention: frame does not fit in shared memory");
-    static int configured_smem = 0;
+    static std::atomic<int> configured_smem{0};  // two host threads may race here: the attribute call is idempotent
     if (smem > configured_smem) {
         CBAS_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured_smem = smem;
@@ -204,7 +205,7 @@ int launch_preprocess_resize(const uint8_t* frames, __nv_bfloat16* A, int n, int
         const int io_bytes = std::max(max_rows * src_pitch, (side / 16) * 1536);
         const size_t smem = (size_t)io_bytes + (size_t)3 * max_rows * side * 4 + 16 * 32 + 32;  // + row taps, + slack for the word-wise reads of the last staged row
         if (smem <= 110 * 1024) {
-            static size_t configured_fast = 0;
+            static std::atomic<size_t> configured_fast{0};
             if (smem > configured_fast) {
                 CBAS_CHECK(cudaFuncSetAttribute(preprocess_resize_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)smem));
@@ -217,7 +218,7 @@ int launch_preprocess_resize(const uint8_t* frames, __nv_bfloat16* A, int n, int
         }
     }
     if (g_resize_tiled && tile_smem <= 200 * 1024 && aligned) {
-        static size_t configured = 0;
+        static std::atomic<size_t> configured{0};
         if (tile_smem > configured) {
             CBAS_CHECK(cudaFuncSetAttribute(preprocess_resize_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)tile_smem));

@@ -1,6 +1,8 @@
 // Host launcher for the tcgen05 GEMM: builds the TMA tensor maps (driver entry point fetched through the
 // runtime, so the library does not link libcuda) and dispatches on tile width and epilogue.
 #include "common.h"
+
+#include <atomic>
 #include "gemm_tcgen05.cuh"
 
 #include <mutex>
@@ -50,7 +52,7 @@ template <int BLOCK_N, int EPI, int CG>
 int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BLOCK_N, CG, gemm_epi_double_stage(EPI)>;
     auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI, CG>;
-    static bool configured = false;  // per instantiation
+    static std::atomic<bool> configured{false};  // per instantiation; a race between host threads only repeats the call
     if (!configured) {
         CBAS_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured = true;
