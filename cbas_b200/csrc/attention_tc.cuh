@@ -316,13 +316,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                 }
             }
             *my_max = mx;
-            named_bar_sync(1 + mt, 256);  // the two warpgroups of this query tile
+            named_bar_sync(1 + mt * 4 + quarter, 64);  // only the partner warp: same rows, other half of the keys
             if (stamper) ATC_STAMP(sbase + 1);
             if (warp_has_rows) {
                 mx = fmaxf(mx, *peer_max);
                 const float mc = mx * c;
-                // pass 2: p = exp2(s*c - max*c) two at a time in half precision (ex2.approx.f16x2: the result IS the
-                // f16 tensor-core operand, no repacking), partial row sum, written over the consumed part of S
+                // pass 2: p = exp2(s*c - max*c) (fp32 MUFU, two results packed into one f16 pair: one instruction fewer
+                // per pair than ex2.approx.f16x2, which the hardware splits into two MUFU ops plus a repack), partial
+                // row sum, written over the consumed part of S
                 for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld_32x16(t_row + c0, v);
@@ -335,7 +336,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                             const float x1 = fmaf(__uint_as_float(v[j + 1]), c, -mc);
                             // the MUFU (16 ex2/clk/SM) is the busiest unit of this kernel: the last ATC_POLY_PAIRS
                             // pairs of every 16 go through the FMA-pipe polynomial instead
-                            if ((j >> 1) < 8 - ATC_POLY_PAIRS) pk[j >> 1] = ex2_approx_f16x2(pack_f16(x0, x1));
+                            if ((j >> 1) < 8 - ATC_POLY_PAIRS) pk[j >> 1] = pack_f16(ex2_approx(x0), ex2_approx(x1));  // fp32 MUFU, one pack
                             else pk[j >> 1] = pack_f16(ex2_poly3(x0), ex2_poly3(x1));
                         }
                     } else {
@@ -398,7 +399,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             // which this thread's tile reaches through the max-exchange barrier, i.e. after the wait below.
             fence_proxy_async();
             if (threadIdx.x == 0) ATC_STAMP(19);
-            named_bar_sync(3 + mt, 256);
+            named_bar_sync(9 + mt, 256);
             if (threadIdx.x == 0) ATC_STAMP(20);
             if ((warp & 7) == 0 && mt * 128 < T) {  // first warp of the tile, uniform operands, elected lane
                 if (elect_one()) {

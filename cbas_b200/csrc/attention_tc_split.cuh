@@ -238,7 +238,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
                     }
                 }
                 *my_max = mx;
-                named_bar_sync(1 + pp, 256);
+                named_bar_sync(1 + pp * 4 + quarter, 64);  // only the partner warp: same rows, other half of the block
                 if (warp_has_rows) {
                     mx = fmaxf(mx, *peer_max);  // block max; finite: each half of each block holds keys < T
                     if (half == 0) blockmax[pp * 128 + rit] = mx;
@@ -253,7 +253,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
                             for (int j = 0; j < 16; j += 2) {
                                 const float x0 = fmaf(__uint_as_float(v[j]), c, -mc);
                                 const float x1 = fmaf(__uint_as_float(v[j + 1]), c, -mc);
-                                if ((j >> 1) < 8 - ATC_POLY_PAIRS) pk[j >> 1] = ex2_approx_f16x2(pack_f16(x0, x1));
+                                if ((j >> 1) < 8 - ATC_POLY_PAIRS) pk[j >> 1] = pack_f16(ex2_approx(x0), ex2_approx(x1));  // fp32 MUFU, one pack
                                 else pk[j >> 1] = pack_f16(ex2_poly3(x0), ex2_poly3(x1));
                             }
                         } else {
@@ -327,7 +327,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
                 // one TMA store per query tile; the staging rows of tile qt are rewritten one item later, after this
                 // thread has passed the barrier again, i.e. after the wait on the store's shared-memory read
                 fence_proxy_async();
-                named_bar_sync(3, 256);
+                named_bar_sync(9, 256);
                 if (warp == 8) {
                     if (elect_one()) {
                         if (qt == nq - 1) tma_store_3d(&tmap_o1, ostage + qt * 16384, h * 64, qt * 128, f);
