@@ -81,7 +81,6 @@ SIGNATURES = {
     "cbas_b200_gemm_bf16": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                       c_void_p]),
     "cbas_b200_debug_attention_trace": (C.c_int, [c_void_p]),
-    "cbas_b200_debug_attention_experiment": (C.c_int, [c_int32]),
     "cbas_b200_debug_prune_last_layer": (C.c_int, [c_int32]),
     "cbas_b200_debug_resize_tiled": (C.c_int, [c_int32]),
     "cbas_b200_debug_gemm_cta_group": (C.c_int, [c_int32]),

@@ -55,7 +55,6 @@ struct AttnTcParams {
     const float* rope_cos;     // [T - prefix, 32] fp32 or null (no RoPE in this kernel)
     const float* rope_sin;
     int prefix;
-    int dbg;                   // timing experiments only (0 in production): 1 = PV as SS MMA, 2 = PV with a K-major B
     long long* trace;          // optional [64][ATC_TRACE_SLOTS] clock64 stamps of CTA 0 (profiling aid; null in production)
 };
 

@@ -92,7 +92,6 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* 
 bool g_prune_last_layer = true;  // false: run the last block on every token (test knob)
 int g_resize_tiled = 2;  // test knob: 0 per-pixel kernel, 1 general tiled kernel, 2 column-per-thread kernel when it applies
 long long* g_attention_trace = nullptr;  // device buffer [64][ATC_TRACE_SLOTS] for the stage-timing aid (tools/attn_trace.py)
-int g_attention_dbg = 0;  // AttnTcParams::dbg (timing experiments)
 int g_attention_impl = 0;  // 0 auto (tcgen05 when T <= 256), 1 mma.sync, 2 tcgen05 (both rotate q,k in their prologue)
 
 bool attention_tc_fits(int T, int prefix) {
@@ -138,7 +137,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const floa
             configured_split = smem;
         }
         AttnTcParams p{qkv, out, frames, heads, T, TK, D, 0.125f * 1.4426950408889634f, rope ? cs : nullptr,
-                       rope ? sn : nullptr, prefix, 0, nullptr};
+                       rope ? sn : nullptr, prefix, nullptr};
         const int items = frames * heads;
         const int grid = items < sm_count() ? items : sm_count();
         attention_tc_split_kernel<<<grid, ATC_THREADS, smem, s>>>(tq, tk0, tk1, to, to1, p);
@@ -166,7 +165,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const floa
         configured_smem = smem;
     }
     AttnTcParams p{qkv, out, frames, heads, T, TK, D, 0.125f * 1.4426950408889634f, rope ? cs : nullptr,
-                   rope ? sn : nullptr, prefix, g_attention_dbg, g_attention_trace};
+                   rope ? sn : nullptr, prefix, g_attention_trace};
     const int items = frames * heads;
     const int grid = items < sm_count() ? items : sm_count();
     attention_tc_kernel<<<grid, ATC_THREADS, smem, s>>>(tq, tkv, to, to1, p);
@@ -528,10 +527,6 @@ int cbas_b200_attention_tc(const void* qkv_bf16_dev, void* out_bf16_dev, const f
                                rope_sin_dev, frames, T, prefix, heads, (cudaStream_t)stream);
 }
 
-int cbas_b200_debug_attention_experiment(int mode) {
-    g_attention_dbg = mode;
-    return 0;
-}
 int cbas_b200_debug_attention_trace(void* trace_dev) {
     g_attention_trace = (long long*)trace_dev;
     return 0;

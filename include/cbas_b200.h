@@ -107,8 +107,6 @@ int cbas_b200_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_
 /* Profiling aid: device buffer of 64*16 int64 that CTA 0 of the tcgen05 attention kernel fills with clock64()
  * stamps per pipeline stage (null switches it off). */
 int cbas_b200_debug_attention_trace(void* trace_dev);
-/* timing experiments on the attention kernel (results are wrong for mode != 0); tools/attn_trace.py */
-int cbas_b200_debug_attention_experiment(int mode);
 /* Test knob: 1 (default) = in the last block compute only what the pooled CLS row needs (K/V for all tokens, the
  * rest for the CLS rows), 0 = run the last block on every token.  Same result for the row that is kept. */
 int cbas_b200_debug_prune_last_layer(int32_t on);

@@ -15,16 +15,12 @@ names = {0: "mma0:top", 1: "mma0:S", 2: "mma0:PV", 3: "mma1:top", 4: "mma1:S", 5
          11: "sm1:s_full", 12: "sm1:max", 13: "sm1:p_full", 14: "sm1:o_full", 15: "sm1:done",
          16: "rot:start", 17: "rot:done", 18: "sm0:o_loaded", 19: "sm0:staged", 20: "sm0:bar", 21: "mma0:S_go",
          22: "mma0:PV_go"}
-modes = [int(a) for a in sys.argv[1:]] or [0]
-for mode in modes:
+for mode in [0]:
     tr = torch.zeros(64 * S, dtype=torch.int64, device="cuda")
-    _lib.lib().cbas_b200_debug_attention_experiment(mode)
     _lib.lib().cbas_b200_debug_attention_trace(tr.data_ptr())
     attention_tc(qkv, frames, T, heads, cos, sin, 5); torch.cuda.synchronize()
     _lib.lib().cbas_b200_debug_attention_trace(None)
-    _lib.lib().cbas_b200_debug_attention_experiment(0)
     t = tr.cpu().numpy().reshape(64, S)
-    print("experiment mode", mode)
     for it in range(4, 10):
         print("item", it, " ".join(f"{n}={t[it, i] - t[it, 0]}" for i, n in names.items()), " | item period", t[it + 1, 0] - t[it, 0])
     print("  mean S issue", np.mean(t[4:40, 1] - t[4:40, 21]), "mean PV issue", np.mean(t[4:40, 2] - t[4:40, 22]),
