@@ -92,6 +92,38 @@ def test_encode_file_from_mp4_with_parallel_decode(tmp_path, monkeypatch):
     assert np.abs(outs[0].astype(np.float32) - direct.astype(np.float32)).max() <= 2e-3 * np.abs(direct.astype(np.float32)).max()
 
 
+def test_baseline_config0_vits16_256px_then_head(tmp_path, monkeypatch):
+    """BASELINE configs[0] (the reference's CPU-runnable case): DINOv3 ViT-S/16 on a 256x256 clip in the reference's
+    preprocessing (green/255, native resolution: 261 tokens per frame -> the key-split attention kernel), batches of
+    32, then the LSTM head with in_features = 384 on the stored f16 rows.  The clip is 48 frames instead of 300 so that
+    the fp32 CPU oracle finishes in seconds; nothing in the path depends on the clip length."""
+    model = oenc.build_hf_model("vits16", seed=3, init_scale=3.0)
+    frames = oenc.synthetic_frames(48, 256, 256, seed=31)
+    clip = str(tmp_path / "cam3_00001.npy")
+    np.save(clip, frames)
+    monkeypatch.setattr(gui_state, "proj", None)
+    monkeypatch.setattr(cbas, "CHUNK_SIZE", 32)
+    enc = DinoEncoder.from_hf_model(model, "cuda", max_frames=32)
+    out = cbas.encode_file(enc, clip)
+    with store.EmbeddingReader(out) as r:
+        assert r.shape == (48, 384)
+        emb = r.read(0, 48)
+    want = oenc.encode(model, frames, mode="reference", batch=32)
+    e32 = emb.astype(np.float32)
+    rel = np.abs(e32 - want).max() / np.abs(want).max()
+    cos = (e32 * want).sum(1) / (np.linalg.norm(e32, axis=1) * np.linalg.norm(want, axis=1))
+    print(f"[parity] configs[0] ViT-S/16 @256: min cosine {cos.min():.6f} max|d|/max|ref| {rel:.3e}")
+    assert cos.min() >= 0.999 and rel <= 2e-2
+    sd = ohead.make_head_state(384, 9, 128, 64, seed=8, scale=2.0)
+    head = ClassifierLSTMDeltas(384, 9, seq_len=31)
+    head.load_state_dict(sd)
+    csv = cbas.infer_file(out, head, "m", BEHAVIORS, 31, device=torch.device("cuda"))
+    import pandas as pd
+    got = pd.read_csv(csv).to_numpy()
+    want_p = ohead.infer_windows(emb, sd, seq_len=31)
+    assert np.abs(got - want_p).max() <= 1e-3 and (got.argmax(1) == want_p.argmax(1)).all()
+
+
 def test_worker_threads_encode_then_classify(tmp_path, monkeypatch):
     frames = oenc.synthetic_frames(40, 64, 64, seed=12)
     clips = []
