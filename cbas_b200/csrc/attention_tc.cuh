@@ -7,13 +7,14 @@
 //              O_mt = P_mt V    (128 x 64 x TK, f16 operands) with P read FROM TMEM (f16 pairs written over S
 //              by the softmax warps) and V consumed MN-major exactly as TMA laid it down - no transposes, no P
 //              in shared memory.  V arrives as IEEE f16 (the QKV GEMM stores that third of its output as f16,
-//              EPI_BIAS_BF16_VF16) so the probabilities can stay in the f16 the MUFU produces.
+//              EPI_BIAS_BF16_VF16) so the probabilities can be f16 (11 mantissa bits) rather than bf16.
 //   softmax  : four warpgroups, two per query tile; a thread owns one query row and HALF of its keys (TMEM lane
 //              access is tied to warp_id % 4, so two warps share each lane quarter).  Pass 1 reads S for the
 //              partial row max (exchanged with the partner thread through shared memory), pass 2 re-reads S,
-//              exponentiates (exp2, scale folded), packs bf16 pairs and stores them over consumed columns of S.
+//              exponentiates (exp2, scale folded), packs f16 pairs and stores them over consumed columns of S.
 //   epilogue : each of the two threads of a row scales 32 of the 64 output columns by 1 / (sum_a + sum_b)
-//              -> bf16 -> [M, D] at column head*64.
+//              -> bf16 -> a swizzled shared-memory staging row; one 3-D TMA store per query tile writes
+//              [rows, 64] at column head*64, clipped at the end of the frame.
 //
 //   RoPE     : attention prologue, in shared memory, by FOUR DEDICATED WARPS: as soon as Q and K of an item have
 //              landed they rotate the patch-token rows in place (rotate-half form, fp32 math, cos/sin held as
@@ -24,7 +25,8 @@
 //              skip RoPE.)
 //   overlap  : each query tile has its OWN MMA-issuing warp and its own barrier chain
 //              (S -> softmax -> P V -> epilogue -> next S); tile 1 is started half an item late, so while one
-//              tile's warps are in the MUFU-bound softmax the other tile's MMAs, TMEM drain and global stores run.
+//              tile's warps are in their softmax the other tile's MMAs, TMEM drain and stores run.  The MMA and TMA
+//              warps run warp-uniform code with one elected lane (descriptors in uniform registers).
 //
 // TMEM map (512 columns): query tile mt owns columns [256*mt, 256*mt+256): S at +0..TK; P (f16 pairs) of the
 // first key half at +0..CA/2 and of the second half at +CA..+CA+(TK-CA)/2; O at +192..+256 (written only after
