@@ -4,8 +4,6 @@
 // (modeling_dinov3_vit.py:530-555).  Residual stream is fp32; GEMM operands are bf16 with fp32 accumulation.
 #include "../../include/cbas_b200.h"
 #include "attention.cuh"
-#include <algorithm>
-#include <atomic>
 #include "attention_tc.cuh"
 #include "attention_tc_split.cuh"
 #include "common.h"
@@ -13,6 +11,8 @@
 #include "layernorm.cuh"
 #include "preprocess.cuh"
 
+#include <algorithm>
+#include <atomic>
 #include <vector>
 
 using namespace cbas;

@@ -5,11 +5,12 @@
 //   accumulators in TMEM, double-buffered) -> tcgen05.ld -> epilogue math in registers -> swizzled
 //   shared-memory slab -> TMA store (or TMA add-reduction into the fp32 residual stream) -> global.
 //
-// Warp roles (one CTA per SM, 512 + 128 threads).  The single-thread roles sit in the HIGHEST warp ids: the warp
-// scheduler favours higher warp ids among ready warps, so the TMA/MMA issue threads are never starved by sixteen
-// epilogue warps crunching GELU in the same sub-partitions.
-//   warp 16  : TMA producer (one elected lane)
-//   warp 17  : MMA issuer   (one elected lane)
+// Warp roles (one CTA per SM, 512 + 128 threads).  The issuing roles run WARP-UNIFORM code with one elected lane
+// (ptx.cuh::elect_one): inside an `if (lane == 0)` region the compiler cannot keep descriptors in uniform registers
+// and wraps every tcgen05.mma / TMA instruction in an ELECT + R2UR waterfall of ~100 cycles, which starved the MMA
+// issue next to sixteen epilogue warps crunching GELU in the same sub-partitions.
+//   warp 16  : TMA producer (whole warp walks the loop, one elected lane issues)
+//   warp 17  : MMA issuer   (same; with CTA pairs only the leader CTA's warp issues)
 //   warp 18  : TMEM allocator / deallocator
 //   warp 19  : idle
 //   warps 0-15: epilogue, two groups of eight warps.  Warp w may only read TMEM lanes 32*(w%4)..+31, so a group
