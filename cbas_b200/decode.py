@@ -85,7 +85,14 @@ class ParallelVideoReader:
             self._free.append(self._held.pop(0))
         self._pump()
         while k not in self._done:
-            index, slot, n, err = self._results.get()
+            try:
+                index, slot, n, err = self._results.get(timeout=2.0)
+            except Exception:  # queue.Empty: make sure somebody is still decoding
+                dead = [p.exitcode for p in self._procs if not p.is_alive()]
+                if dead:
+                    self.close()
+                    raise RuntimeError(f"a decode worker of '{self.path}' exited unexpectedly (exit codes {dead})")
+                continue
             if err is not None:
                 self.close()
                 raise RuntimeError(f"decode worker failed on chunk {index} of '{self.path}':\n{err}")
