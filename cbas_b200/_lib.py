@@ -87,6 +87,7 @@ SIGNATURES = {
     "cbas_b200_layernorm": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
     "cbas_b200_attention": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                       c_void_p]),
+    "cbas_b200_attention_tc_supported": (C.c_int, [c_int32, c_int32, c_int32]),
     "cbas_b200_attention_tc": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                          c_void_p]),
     "cbas_b200_debug_attention_impl": (C.c_int, [c_int32]),

@@ -456,7 +456,7 @@ int cbas_b200_encoder_create(const cbas_encoder_cfg* cfg, const cbas_encoder_wei
     e->T = e->Np + cfg->prefix_tokens;
     if (3 * ((e->T + 15) & ~15) * 128 > 232448) {
         delete e;
-        return fail("too many tokens per frame: the attention kernels keep a frame's K and V in shared memory (T <= 605)");
+        return fail("too many tokens per frame: the attention kernels keep a frame's K and V in shared memory (T <= 592)");
     }
     e->Kp = ((cfg->mode == CBAS_PRE_REFERENCE ? P * P : 3 * P * P) + 63) & ~63;
     const size_t mt = (size_t)cfg->max_frames * e->T, D = cfg->hidden;
@@ -552,6 +552,10 @@ int cbas_b200_layernorm(const float* in_dev, const float* gamma_dev, const float
                         int32_t rows, int32_t D, float eps, void* stream) {
     return launch_layernorm<__nv_bfloat16>(in_dev, 1, gamma_dev, beta_dev, (__nv_bfloat16*)out_bf16_dev, rows, D, eps,
                                            (cudaStream_t)stream);
+}
+
+int cbas_b200_attention_tc_supported(int32_t T, int32_t prefix, int32_t rope) {
+    return (attention_tc_fits(T, prefix) || attention_tc_split_fits(T, prefix, rope != 0)) ? 1 : 0;
 }
 
 int cbas_b200_attention(const void* qkv_bf16_dev, void* out_bf16_dev, const float* rope_cos_dev,

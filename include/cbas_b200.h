@@ -120,6 +120,9 @@ int cbas_b200_layernorm(const float* in_dev, const float* gamma_dev, const float
 int cbas_b200_attention(const void* qkv_bf16_dev, void* out_bf16_dev, const float* rope_cos_dev,
                         const float* rope_sin_dev, int32_t frames, int32_t T, int32_t prefix, int32_t heads,
                         void* stream);
+/* 1 when a tcgen05 attention kernel covers frames of T tokens (shared-memory and TMEM budget), else 0: the encoder
+ * then uses cbas_b200_attention (mma.sync).  `rope` != 0: with RoPE tables. */
+int cbas_b200_attention_tc_supported(int32_t T, int32_t prefix, int32_t rope);
 /* tcgen05 attention (frames of <= 256 tokens).  q and k are bf16, the V third of the buffer is IEEE f16 (that is how
  * the encoder's QKV GEMM stores it for this kernel).  RoPE is applied in the kernel's prologue from the given tables
  * ([T - prefix, 32] f32); pass null tables to skip the rotation. */

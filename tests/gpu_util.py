@@ -33,7 +33,9 @@ def layernorm(x_f32, g, b, eps=1e-5):
 def attention(qkv_bf16, cos, sin, frames, T, prefix, heads):
     D = heads * 64
     out = torch.empty(frames * T, D, device="cuda", dtype=torch.bfloat16)
-    _lib.check(_lib.lib().cbas_b200_attention(qkv_bf16.data_ptr(), out.data_ptr(), cos.data_ptr(), sin.data_ptr(),
+    _lib.check(_lib.lib().cbas_b200_attention(qkv_bf16.data_ptr(), out.data_ptr(),
+                                              cos.data_ptr() if cos is not None else None,
+                                              sin.data_ptr() if sin is not None else None,
                                               frames, T, prefix, heads, stream()), "attention")
     return out
 

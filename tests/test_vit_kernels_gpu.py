@@ -116,6 +116,43 @@ def test_attention_tcgen05_key_split(T, heads, frames, rope_side):
     assert torch.isfinite(out).all()
 
 
+@pytest.mark.parametrize("impl", [0, 1], ids=["auto_tcgen05", "mma_sync"])
+def test_attention_every_token_count_residue(impl):
+    """Token counts sweeping every residue mod 16 and both sides of every kernel boundary (one tile / two tiles /
+    key-split / mma.sync-only), without RoPE and with a synthetic table: masks, partial tiles, clipped stores."""
+    _lib.check(_lib.lib().cbas_b200_debug_attention_impl(impl), "attention_impl")
+    try:
+        heads, frames, P = 6, 3, 5
+        D = heads * 64
+        worst = 0.0
+        for T in [6, 17, 31, 64, 100, 127, 128, 129, 143, 160, 177, 191, 206, 222, 239, 255, 256, 257, 270, 288, 303,
+                  319, 336, 350, 367, 384, 385, 430, 512, 592]:
+            for with_rope in (False, True):
+                qkv, x = _qkv_with_f16_v(frames, T, D, heads)
+                if with_rope:
+                    ang = torch.rand(T - P, 32, device="cuda") * 6.28
+                    cos, sin = torch.cos(ang).contiguous(), torch.sin(ang).contiguous()
+                    q, k = _rope_ref(x[0], x[1], cos, sin)
+                else:
+                    cos = sin = None
+                    q, k = x[0], x[1]
+                if impl == 1 or not _lib.lib().cbas_b200_attention_tc_supported(T, P, 1 if with_rope else 0):
+                    vb = x[2].permute(0, 2, 1, 3).reshape(frames * T, D).to(torch.bfloat16)
+                    buf = torch.cat([qkv[:, :2 * D], vb], dim=1).contiguous()
+                    v_ref = vb.float().view(frames, T, heads, 64).permute(0, 2, 1, 3)
+                    out = attention(buf, cos, sin, frames, T, P, heads).float()
+                else:
+                    v_ref = x[2]
+                    out = attention_tc(qkv, frames, T, heads, cos, sin, P).float()
+                want = F.scaled_dot_product_attention(q, k, v_ref, scale=0.125).permute(0, 2, 1, 3).reshape(frames * T, D)
+                e = rel_err(out, want)
+                worst = max(worst, e)
+                assert torch.isfinite(out).all() and e < 1.5e-2, f"T={T} rope={with_rope}: rel err {e}"
+        print(f"[parity] attention sweep impl {impl}: worst rel err {worst:.3e}")
+    finally:
+        _lib.lib().cbas_b200_debug_attention_impl(0)
+
+
 def test_rope_tables_match_hf_module():
     from transformers import DINOv3ViTConfig
     from transformers.models.dinov3_vit.modeling_dinov3_vit import DINOv3ViTRopePositionEmbedding
