@@ -101,6 +101,22 @@ def test_head_variants_fixture_from_reference(golden_dir, name):
     _check_probs(probs, want, f"head variant {name}")
 
 
+@pytest.mark.parametrize("seq,cw,C,F,hs,layers", [(95, 5, 9, 768, 64, 1), (63, 9, 32, 384, 128, 1), (3, 5, 1, 64, 64, 2),
+                                                  (5, 1, 2, 128, 128, 2), (31, 0, 9, 768, 64, 1), (11, 20, 3, 256, 64, 1)])
+def test_head_hyperparameter_corners(seq, cw, C, F, hs, layers):
+    """Corners of the head's configuration space: the sweep's long windows (63 / 95, sweep_runner.py:110), the shortest
+    legal window, a centre window wider than the sequence (clipped to it) and of a single frame, 1 and 32 behaviours."""
+    sd = ohead.make_head_state(F, C, 128, hs, seed=seq + C, scale=1.5, lstm_layers=layers)
+    n = 150
+    emb = (np.random.default_rng(seq).standard_normal((n, F)) * 1.1).astype(np.float16)
+    head = _head(sd, in_features=F, out_features=C, seq_len=seq, center_window_size=cw, lstm_hidden_size=hs,
+                 lstm_layers=layers)
+    probs, logits = head.infer_embeddings(torch.from_numpy(emb).cuda(), temperature=0.8, return_logits=True)
+    want, want_logits = ohead.infer_windows(emb, sd, seq_len=seq, temperature=0.8, return_logits=True, center_window=cw)
+    np.testing.assert_allclose(logits.cpu().numpy(), want_logits, atol=3e-4, rtol=3e-4)
+    _check_probs(probs.cpu().numpy(), want, f"head corner T{seq} cw{cw} C{C} F{F} Hs{hs} L{layers}")
+
+
 @pytest.mark.parametrize("n", [1, 5, 15, 16, 31])
 def test_short_videos_are_all_padding(n):
     sd = ohead.make_head_state(768, 9, 128, 64, seed=3)
