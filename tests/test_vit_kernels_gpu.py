@@ -153,6 +153,42 @@ def test_attention_every_token_count_residue(impl):
         _lib.lib().cbas_b200_debug_attention_impl(0)
 
 
+def test_preprocess_strided_and_unaligned_frames():
+    """Frames that are views into a larger buffer: odd base offset, padded rows, padded frames (the C ABI takes byte
+    strides; the vectorised paths must fall back where 16-byte alignment does not hold)."""
+    H, W, n, S = 96, 128, 3, 64
+    frames = oenc.synthetic_frames(n, H, W, seed=4, structured=False)
+    rs, fs, off = W * 3 + 7, (W * 3 + 7) * H + 29, 3
+    buf = torch.zeros(off + n * fs + 64, dtype=torch.uint8)
+    for f in range(n):
+        for y in range(H):
+            o = off + f * fs + y * rs
+            buf[o:o + W * 3] = torch.from_numpy(frames[f, y].reshape(-1))
+    buf = buf.cuda()
+    base = buf.data_ptr() + off
+    # green
+    A = torch.empty(n * (H // 16) * (W // 16), 256, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().cbas_b200_preprocess_green(base, A.data_ptr(), n, H, W, fs, rs, stream()), "green")
+    g = torch.from_numpy(frames[..., 1].astype(np.float32))
+    want = g.view(n, H // 16, 16, W // 16, 16).permute(0, 1, 3, 2, 4).reshape(-1, 256)
+    assert torch.equal(A.float().cpu(), want)
+    # resize + normalise: same result as from a contiguous copy
+    ymin, wy = aa_bilinear_taps(H, S)
+    xmin, wx = aa_bilinear_taps(W, S)
+    t = lambda a, dt: torch.from_numpy(a).to("cuda", dt).contiguous()
+    ymin_d, wy_d, xmin_d, wx_d = t(ymin, torch.int32), t(wy, torch.float32), t(xmin, torch.int32), t(wx, torch.float32)
+    ns = S // 16
+    outs = []
+    fc = torch.from_numpy(frames).cuda()
+    for ptr, fstride, rstride in ((base, fs, rs), (fc.data_ptr(), H * W * 3, W * 3)):
+        B = torch.empty(n * ns * ns, 768, device="cuda", dtype=torch.bfloat16)
+        _lib.check(_lib.lib().cbas_b200_preprocess_resize(
+            ptr, B.data_ptr(), n, H, W, fstride, rstride, S, ymin_d.data_ptr(), wy_d.data_ptr(), wy.shape[1],
+            xmin_d.data_ptr(), wx_d.data_ptr(), wx.shape[1], stream()), "resize")
+        outs.append(B.float().cpu())
+    assert float((outs[0] - outs[1]).abs().max()) <= 2.0 ** -7  # per-pixel kernel vs tiled kernel: <= 1 bf16 ulp
+
+
 def test_rope_tables_match_hf_module():
     from transformers import DINOv3ViTConfig
     from transformers.models.dinov3_vit.modeling_dinov3_vit import DINOv3ViTRopePositionEmbedding
