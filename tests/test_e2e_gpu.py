@@ -160,3 +160,50 @@ def test_worker_threads_encode_then_classify(tmp_path, monkeypatch):
         df = pd.read_csv(w)
         assert list(df.columns) == ["a", "b", "c", "d"] and len(df) == 20
         np.testing.assert_allclose(df.to_numpy().sum(1), 1.0, atol=1e-5)
+
+
+def test_two_host_threads_on_their_own_streams():
+    """SURVEY 8b threading contract: EncodeThread and ClassificationThread call into the library concurrently, each
+    inside `with torch.cuda.stream(own_stream)`.  Both must get exactly the results they get alone."""
+    import threading
+    enc = DinoEncoder("synthetic:vits16@2", "cuda", max_frames=16)
+    frames = torch.from_numpy(oenc.synthetic_frames(16, 224, 224, seed=41)).cuda()
+    sd = ohead.make_head_state(384, 9, 128, 64, seed=9, scale=2.0)
+    head = ClassifierLSTMDeltas(384, 9, seq_len=31)
+    head.load_state_dict(sd)
+    head = head.to("cuda").eval()
+    emb = torch.randn(5000, 384, device="cuda").half()
+    want_e = enc.encode_u8(frames).clone()
+    want_p = head.infer_embeddings(emb).clone()
+    torch.cuda.synchronize()
+    errors = []
+
+    def encode_loop():
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(25):
+                    got = enc.encode_u8(frames)
+                    s.synchronize()
+                    assert torch.equal(got, want_e)
+        except Exception as e:  # noqa: BLE001
+            errors.append(("encode", repr(e)))
+
+    def classify_loop():
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(25):
+                    got = head.infer_embeddings(emb)
+                    s.synchronize()
+                    assert torch.equal(got, want_p)
+        except Exception as e:  # noqa: BLE001
+            errors.append(("classify", repr(e)))
+
+    ts = [threading.Thread(target=encode_loop), threading.Thread(target=classify_loop)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in ts), "a worker thread hung"
+    assert not errors, errors
