@@ -207,3 +207,39 @@ def test_two_host_threads_on_their_own_streams():
         t.join(timeout=120)
     assert not any(t.is_alive() for t in ts), "a worker thread hung"
     assert not errors, errors
+
+
+def test_launcher_two_ranks_share_the_work(tmp_path):
+    """cbas_b200.launch under torchrun with two ranks (both on GPU 0, gloo for the one collective): the videos are
+    split between the ranks, every video ends up encoded and classified exactly once, the reduced actogram equals
+    the single-process one, and a second run finds nothing left to do (file-level resume)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    vids = tmp_path / "rec"
+    vids.mkdir()
+    for i, n in enumerate((40, 25, 33, 18, 29)):
+        np.save(str(vids / f"cam{i}_00001.npy"), oenc.synthetic_frames(n, 64, 64, seed=50 + i))
+    sd = ohead.make_head_state(384, 4, 128, 64, seed=6)
+    head = ClassifierLSTMDeltas(384, 4, seq_len=31)
+    head.load_state_dict(sd)
+    mdir = str(tmp_path / "models" / "M")
+    bundle.save_model_bundle(mdir, head, "M", ["a", "b", "c", "d"], 31, encoder_model_identifier="synthetic:vits16@4")
+    common = ["--videos", str(vids / "*.npy"), "--encoder", "synthetic:vits16@4", "--model-dir", mdir,
+              "--actogram", "b", "--framerate", "0.05", "--bin-minutes", "3", "--threshold", "0.0"]
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=root, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+
+    two = run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+               "127.0.0.1", "--master-port", "29571", "-m", "cbas_b200.launch", *common, "--backend", "gloo"])
+    assert two["world_size"] == 2 and two["frames"] == 145
+    assert sum(r["encoded"] for r in two["per_rank"]) == 5 and all(r["encoded"] > 0 for r in two["per_rank"])
+    assert sum(r["classified"] for r in two["per_rank"]) == 5
+    again = run([sys.executable, "-m", "cbas_b200.launch", *common])  # single process, everything already on disk
+    assert again["per_rank"][0]["encoded"] == 0 and again["per_rank"][0]["classified"] == 0
+    assert again["actogram"]["bins"] == two["actogram"]["bins"] and sum(two["actogram"]["bins"]) > 0
