@@ -184,6 +184,24 @@ def test_full_chunk_properties_at_baseline_size():
         assert rel_err(enc.encode_u8(frames[i:i + 1]), full[i:i + 1]) < 1e-5  # single-CTA tiles vs CTA pairs
 
 
+@pytest.mark.parametrize("preprocess", ["reference", "processor"])
+def test_degenerate_frames(preprocess):
+    """All-black, all-white and single-colour frames (a covered lens, a saturated sensor): finite output that matches
+    the oracle - constant patches give LayerNorm rows with zero variance in the first block's input only through eps."""
+    model = oenc.build_hf_model("vits16", seed=5, init_scale=3.0)
+    frames = np.zeros((4, 64, 64, 3), np.uint8)
+    frames[1] = 255
+    frames[2, :, :, 1] = 128
+    frames[3, ::2] = 255
+    side = 64 if preprocess == "reference" else 48
+    want = oenc.encode(model, frames, mode=preprocess, size=side)
+    enc = DinoEncoder.from_hf_model(model, "cuda", preprocess=preprocess, image_size=side, max_frames=4)
+    got = enc.encode_u8(torch.from_numpy(frames).cuda()).cpu()
+    assert torch.isfinite(got).all()
+    cos, _, rel = _report(f"degenerate frames, {preprocess}", got, want)
+    assert cos >= 0.999 and rel <= 2e-2
+
+
 def test_empty_batch():
     enc = DinoEncoder("synthetic:vits16", "cuda", max_frames=4)
     out = enc.encode_u8(torch.zeros(0, 64, 64, 3, dtype=torch.uint8, device="cuda"))
