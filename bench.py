@@ -32,21 +32,27 @@ SIDE = 224
 METRIC = "frames_per_sec_encoded_dinov3_vitb16_224px"
 
 
-def flops_per_frame(D, L, I, side):
-    """Dense forward FLOPs: 2*[Np*768*D + L*(4*N*D^2 + 2*N^2*D + 2*N*D*I)], N = Np + 5."""
-    Np = (side // 16) ** 2
+def metric_name(arch):
+    """BASELINE.json's metric for the default arch; the same pattern for the others."""
+    return METRIC.replace("dinov3_vitb16", arch.replace("-", "_") if arch.startswith("dinov2") else f"dinov3_{arch}")
+
+
+def flops_per_frame(D, L, I, side, patch=16):
+    """Dense forward FLOPs: 2*[Np*3*P^2*D + L*(4*N*D^2 + 2*N^2*D + 2*N*D*I)], N = Np + 5
+    (P = 16: the patch term is Np*768*D)."""
+    Np = (side // patch) ** 2
     N = Np + 5
-    return 2.0 * (Np * 768 * D + L * (4 * N * D * D + 2 * N * N * D + 2 * N * D * I))
+    return 2.0 * (Np * 3 * patch * patch * D + L * (4 * N * D * D + 2 * N * N * D + 2 * N * D * I))
 
 
-def flops_per_frame_executed(D, L, I, side):
+def flops_per_frame_executed(D, L, I, side, patch=16):
     """FLOPs actually issued: the last block projects K and V for every token but runs the query, attention, proj
     and MLP for the CLS row only (the other rows of the final hidden state are never read, cbas.py:677)."""
-    Np = (side // 16) ** 2
+    Np = (side // patch) ** 2
     N = Np + 5
     layer = 2.0 * (4 * N * D * D + 2 * N * N * D + 2 * N * D * I)
     last = 2.0 * (2 * N * D * D + 2 * D * D + 2 * N * D + 2 * D * I)
-    return flops_per_frame(D, L, I, side) - layer + last
+    return flops_per_frame(D, L, I, side, patch) - layer + last
 
 
 def load_peaks():
@@ -137,7 +143,7 @@ def run_reference(args, rank):
     fpst = 4
     fps, dt, threads, done = cpu_reference_fps(fpst, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC.replace("vitb16", args.arch), "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args.arch), "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "DINOv3 ViT-B/16 224px streamed encode of a synthetic 10-min 30fps 256x256 clip "
@@ -391,7 +397,7 @@ def main():
     with contextlib.redirect_stdout(sys.stderr):  # stdout carries exactly one JSON line
         enc = DinoEncoder(f"synthetic:{args.arch}", dev, preprocess=args.preprocess, image_size=side, max_frames=CHUNK)
     a = ARCHITECTURES[args.arch]
-    F = flops_per_frame(a["hidden_size"], a["num_hidden_layers"], a["intermediate_size"], side)
+    F = flops_per_frame(a["hidden_size"], a["num_hidden_layers"], a["intermediate_size"], side, a.get("patch_size", 16))
     peaks = load_peaks()
 
     # the clip: K distinct chunks when memory allows (inputs >> L2), at most the 36 chunks of the 10-min clip
@@ -440,10 +446,11 @@ def main():
     # ---- roofline of the dominant kernel (largest share of device time in the timed region)
     total_prof_ms = sum(v[0] for v in prof.values())
     dom = max(prof, key=lambda k: prof[k][0])
-    M = CHUNK * ((side // 16) ** 2 + 5)
+    P = a.get("patch_size", 16)
+    M = CHUNK * ((side // P) ** 2 + 5)
     D, I = a["hidden_size"], a["intermediate_size"]
     gemm_flops = {"qkv_gemm": 2.0 * M * 3 * D * D, "proj_gemm": 2.0 * M * D * D, "up_gemm": 2.0 * M * I * D,
-                  "down_gemm": 2.0 * M * D * I, "patch_gemm": 2.0 * CHUNK * (side // 16) ** 2 * 768 * D}
+                  "down_gemm": 2.0 * M * D * I, "patch_gemm": 2.0 * CHUNK * (side // P) ** 2 * 3 * P * P * D}
     breakdown = {k: {"ms_per_step": v[0] / K, "launches_per_step": v[1] / K, "share": v[0] / total_prof_ms}
                  for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     if dom in gemm_flops:
@@ -460,12 +467,12 @@ def main():
     else:
         # HBM-bound kernels: algorithmic bytes per launch
         bytes_alg = {"attention": M * 3 * D * 2 + M * D * 2, "layernorm": M * D * (4 + 2),
-                     "preprocess": CHUNK * (src_hw[0] * src_hw[1] * 3 + (side // 16) ** 2 * 768 * 2)}.get(dom)
+                     "preprocess": CHUNK * (src_hw[0] * src_hw[1] * 3 + (side // P) ** 2 * 3 * P * P * 2)}.get(dom)
         ach = bytes_alg / (prof[dom][0] / prof[dom][1] / 1000.0) / 1e9 if bytes_alg else None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": ach / peaks["hbm"] if ach else None, "traffic": None,
                     "share_of_step": prof[dom][0] / total_prof_ms}
-    Fx = flops_per_frame_executed(a["hidden_size"], a["num_hidden_layers"], a["intermediate_size"], side)
+    Fx = flops_per_frame_executed(a["hidden_size"], a["num_hidden_layers"], a["intermediate_size"], side, a.get("patch_size", 16))
     forward = {"gflop_per_frame_dense": F / 1e9, "gflop_per_frame_executed": Fx / 1e9,
                "note": "tflops / frac use the DENSE count (SURVEY 8d); executed is lower because the last block "
                        "only computes what the pooled CLS row needs",
@@ -515,12 +522,12 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": METRIC.replace("vitb16", args.arch), "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric_name(args.arch), "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"DINOv3 {args.arch} {side}px streamed encode of a synthetic 10-min 30fps "
+            "config": {"workload": f"{'DINOv2-with-registers' if args.arch.startswith('dinov2') else 'DINOv3'} {args.arch} {side}px streamed encode of a synthetic 10-min 30fps "
                                    f"{src_hw[0]}x{src_hw[1]} uint8 clip, {CHUNK}-frame chunks (BASELINE configs[1])",
-                       "preprocess": args.preprocess, "chunk_frames": CHUNK, "tokens_per_frame": (side // 16) ** 2 + 5,
+                       "preprocess": args.preprocess, "chunk_frames": CHUNK, "tokens_per_frame": (side // a.get("patch_size", 16)) ** 2 + 5,
                        "parallelism": f"dp{world} (one clip per GPU, no collective)",
                        "l2": f"{n_chunks} distinct {CHUNK * src_hw[0] * src_hw[1] * 3 >> 20} MiB input chunks and "
                              f">1 GiB of activations per step: far larger than the 126 MB L2",
