@@ -39,8 +39,9 @@ def _report(tag, got, want):
 @pytest.mark.parametrize("arch,side,n,scale", [("vits16", 64, 5, 4.0), ("vitb16", 224, 4, 3.0), ("vitb16", 256, 3, 1.0),
                                               ("vitl16", 96, 3, 2.0)])
 def test_reference_mode_parity(arch, side, n, scale, attention_impl):
-    if attention_impl >= 2 and not (128 <= side <= 256):
-        pytest.skip("tcgen05 attention covers frames of 49..384 tokens")
+    from cbas_b200 import _lib
+    if attention_impl >= 2 and not _lib.lib().cbas_b200_attention_tc_supported((side // 16) ** 2 + 5, 5, 1):
+        pytest.skip("no tcgen05 attention kernel for this token count")
     model = oenc.build_hf_model(arch, seed=0, init_scale=scale)
     frames = oenc.synthetic_frames(n, side, side, seed=5)
     want = oenc.encode(model, frames, mode="reference")
