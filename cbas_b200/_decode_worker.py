@@ -8,11 +8,12 @@ from multiprocessing import shared_memory
 import numpy as np
 
 
-def run(path: str, shm_name: str, slots: int, chunk: int, h: int, w: int, tasks, results) -> None:
+def run(path: str, shm_name: str, slots: int, chunk: int, h: int, w: int, green_only: bool, tasks, results) -> None:
     import cv2
     shm = shared_memory.SharedMemory(name=shm_name)
     try:
-        ring = np.ndarray((slots, chunk, h, w, 3), dtype=np.uint8, buffer=shm.buf)
+        shape = (slots, chunk, h, w) if green_only else (slots, chunk, h, w, 3)
+        ring = np.ndarray(shape, dtype=np.uint8, buffer=shm.buf)
         cap = cv2.VideoCapture(path)
         pos = 0
         while True:
@@ -24,12 +25,17 @@ def run(path: str, shm_name: str, slots: int, chunk: int, h: int, w: int, tasks,
                 if not cap.isOpened():
                     raise RuntimeError(f"could not open video '{path}'")
                 if start != pos:
-                    cap.set(cv2.CAP_PROP_POS_FRAMES, start)  # exact: FFmpeg backend decodes forward from the keyframe
+                    # the FFmpeg backend seeks to the preceding keyframe and decodes forward to `start`
+                    cap.set(cv2.CAP_PROP_POS_FRAMES, start)
                 for i in range(start, end):
                     ok, bgr = cap.read()
                     if not ok:
                         raise RuntimeError(f"decode failed at frame {i} of '{path}'")
-                    cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB, dst=ring[slot, i - start])
+                    if green_only:
+                        # green is channel 1 in BGR and in RGB alike: no colour conversion, a third of the bytes
+                        np.copyto(ring[slot, i - start], bgr[:, :, 1])
+                    else:
+                        cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB, dst=ring[slot, i - start])
                 pos = end
                 results.put((index, slot, end - start, None))
             except Exception:  # reported to the parent, which raises it in the caller's thread

@@ -13,6 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CBAS_B200_LIB: load another build of the same library (A/B timing of two kernel versions on one GPU box)
 LIB_PATH = os.environ.get("CBAS_B200_LIB") or os.path.join(_HERE, "libcbas_b200.so")
 
+ABI_VERSION = 3  # CBAS_B200_ABI_VERSION in include/cbas_b200.h
+OPT_ATTENTION_IMPL, OPT_PRUNE_LAST_LAYER, OPT_RESIZE_KERNEL = 0, 1, 2  # cbas_b200_encoder_set_option
+
 _lib = None
 _lock = threading.Lock()
 
@@ -30,7 +33,7 @@ class EncoderCfg(C.Structure):
 
 class LayerWeights(C.Structure):
     _fields_ = [(n, c_void_p) for n in (
-        "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b", "w_up", "b_up", "w_down", "b_down")]
+        "w_qkv", "c1_qkv", "b_qkv", "w_o", "b_o", "w_up", "c1_up", "b_up", "w_down", "b_down")]
 
 
 class EncoderWeights(C.Structure):
@@ -75,13 +78,20 @@ SIGNATURES = {
     "cbas_b200_encoder_create": (C.c_int, [C.POINTER(EncoderCfg), C.POINTER(EncoderWeights), C.POINTER(c_void_p)]),
     "cbas_b200_encoder_destroy": (None, [c_void_p]),
     "cbas_b200_encoder_forward_u8": (C.c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
+    "cbas_b200_encoder_forward_u8_plane": (C.c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p,
+                                                     c_void_p]),
     "cbas_b200_encoder_forward_f32": (C.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "cbas_b200_encoder_debug_hidden": (C.c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p,
                                                  c_void_p]),
     "cbas_b200_gemm_bf16": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                       c_void_p]),
+    "cbas_b200_encoder_set_option": (C.c_int, [c_void_p, c_int32, c_int32]),
+    "cbas_b200_ln_stats_init": (C.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "cbas_b200_gemm_resid_ln": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_int32, c_int32, c_int32, c_void_p]),
+    "cbas_b200_gemm_ln_a": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                      c_int32, c_int32, c_float, c_void_p]),
     "cbas_b200_debug_attention_trace": (C.c_int, [c_void_p]),
-    "cbas_b200_debug_prune_last_layer": (C.c_int, [c_int32]),
     "cbas_b200_debug_resize_tiled": (C.c_int, [c_int32]),
     "cbas_b200_debug_gemm_cta_group": (C.c_int, [c_int32]),
     "cbas_b200_layernorm": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
@@ -90,7 +100,6 @@ SIGNATURES = {
     "cbas_b200_attention_tc_supported": (C.c_int, [c_int32, c_int32, c_int32]),
     "cbas_b200_attention_tc": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                          c_void_p]),
-    "cbas_b200_debug_attention_impl": (C.c_int, [c_int32]),
     "cbas_b200_preprocess_green": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_int32,
                                              c_void_p]),
     "cbas_b200_preprocess_resize": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_int32,
@@ -117,11 +126,16 @@ def lib() -> C.CDLL:
                     f"{LIB_PATH} is missing: build it with `python -m cbas_b200.build` "
                     "(cbas_b200 has no CPU fallback)")
             handle = C.CDLL(LIB_PATH)
+            ab_build = bool(os.environ.get("CBAS_B200_LIB"))  # an older build, for kernel-level A/B timing only
             for name, (res, args) in SIGNATURES.items():
-                fn = getattr(handle, name)
+                fn = getattr(handle, name, None)
+                if fn is None:
+                    if ab_build:
+                        continue
+                    raise RuntimeError(f"{LIB_PATH} does not export {name}; rebuild")
                 fn.restype = res
                 fn.argtypes = args
-            if handle.cbas_b200_abi_version() != 2:
+            if handle.cbas_b200_abi_version() != ABI_VERSION and not ab_build:
                 raise RuntimeError("libcbas_b200.so ABI version mismatch; rebuild")
             _lib = handle
     return _lib

@@ -23,12 +23,39 @@ from .classifier_head import ClassifierLSTMDeltas, actogram_bins
 from .encoder import DinoEncoder
 
 CHUNK_SIZE = 512  # cbas.py:48
-# worker processes that decode chunks ahead of encode_file (cbas_b200/decode.py); 0 = decode in the calling thread
-# exactly like the reference.  Set from the environment or by assigning cbas.DECODE_WORKERS.
+# worker processes that decode chunks ahead of encode_file (cbas_b200/decode.py); 0 = decode in the encoding process
+# like the reference (on a helper thread, one chunk ahead), -1 = one worker per host core minus two.
+# Set from the environment or by assigning cbas.DECODE_WORKERS.
 DECODE_WORKERS = int(os.environ.get("CBAS_B200_DECODE_WORKERS", "0"))
 
 
 # ----------------------------------------------------------------------------------------------- video decode
+def _exact_frame_count(cap, path: str) -> int:
+    """Number of frames OpenCV can actually decode.  CAP_PROP_FRAME_COUNT is a container estimate that may exceed it
+    (the reference uses decord's exact len(), cbas.py:402-403); when the estimate's last frame cannot be read, count by
+    grabbing (no pixel decode) so that encode_file never asks for a frame that does not exist."""
+    import cv2
+    est = max(0, int(cap.get(cv2.CAP_PROP_FRAME_COUNT)))
+    if est == 0:
+        return 0
+    cap.set(cv2.CAP_PROP_POS_FRAMES, est - 1)
+    ok = cap.grab()
+    if ok and not cap.grab():
+        cap.set(cv2.CAP_PROP_POS_FRAMES, 0)
+        return est
+    # estimate is off (too long, or too short): count what is there
+    cap.release()
+    cap.open(path)
+    n = 0
+    while cap.grab():
+        n += 1
+    cap.release()
+    cap.open(path)
+    if n != est:
+        print(f"Warning: {os.path.basename(path)}: container reports {est} frames, {n} can be decoded; using {n}.")
+    return n
+
+
 class VideoReader:
     """CPU video decode behind the two calls encode_file makes on decord.VideoReader (cbas.py:402,425):
     len(reader) and reader.get_batch(indices) -> uint8 RGB [n,H,W,3].  Uses decord when it is installed (the
@@ -46,11 +73,13 @@ class VideoReader:
             if self._arr.ndim != 4 or self._arr.shape[-1] != 3 or self._arr.dtype != np.uint8:
                 raise ValueError(f"{path}: expected a uint8 [N,H,W,3] array")
             self._len = int(self._arr.shape[0])
+            self.frame_hw = (int(self._arr.shape[1]), int(self._arr.shape[2]))
             return
         try:
             import decord  # type: ignore
             self._decord = decord.VideoReader(path, ctx=decord.cpu(0))
             self._len = len(self._decord)
+            self.frame_hw = tuple(int(v) for v in self._decord[0].shape[:2]) if self._len else None
             return
         except ImportError:
             pass
@@ -61,7 +90,8 @@ class VideoReader:
         if not cap.isOpened():
             raise RuntimeError(f"could not open video '{path}'")
         self._cap = cap
-        self._len = max(0, int(cap.get(cv2.CAP_PROP_FRAME_COUNT)))
+        self._len = _exact_frame_count(cap, path)
+        self.frame_hw = (int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT)), int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)))
 
     def __len__(self) -> int:
         return self._len
@@ -85,20 +115,68 @@ class VideoReader:
             frames.append(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB))
         return np.stack(frames) if frames else np.zeros((0, 0, 0, 3), np.uint8)
 
+    def read_into(self, start: int, stop: int, out: np.ndarray) -> None:
+        """Frames [start, stop) straight into `out` (uint8 [stop-start,H,W,3], typically pinned staging memory of the
+        streamed pipeline): one copy from the page cache / decoder, none through an intermediate array."""
+        n = stop - start
+        if n <= 0:
+            return
+        green = out.ndim == 3  # [n,H,W]: the caller wants the green plane only
+        if self._arr is not None:
+            src = self._arr[start:stop, :, :, 1] if green else self._arr[start:stop]
+            parts = min(_COPY_THREADS, n)
+            if parts <= 1:
+                np.copyto(out, src)
+                return
+            # numpy releases the GIL for plain copies: a few threads reach memory bandwidth, one does not
+            cuts = [n * i // parts for i in range(parts + 1)]
+            list(_copy_pool().map(lambda ab: np.copyto(out[ab[0]:ab[1]], src[ab[0]:ab[1]]), zip(cuts[:-1], cuts[1:])))
+            return
+        if self._decord is not None:
+            frames = self._decord.get_batch(list(range(start, stop))).asnumpy()
+            np.copyto(out, frames[:, :, :, 1] if green else frames)
+            return
+        import cv2
+        for k, i in enumerate(range(start, stop)):
+            if i != self._pos:
+                self._cap.set(cv2.CAP_PROP_POS_FRAMES, i)
+                self._pos = i
+            ok, bgr = self._cap.read()
+            if not ok:
+                raise RuntimeError(f"decode failed at frame {i} of '{self.path}'")
+            self._pos += 1
+            if green:
+                np.copyto(out[k], bgr[:, :, 1])  # channel 1 is green in BGR and RGB alike
+            else:
+                cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB, dst=out[k])
+
     def close(self):
         if self._cap is not None:
             self._cap.release()
 
 
+_COPY_THREADS = max(1, min(4, (os.cpu_count() or 1) // 2))
+_pool = None
+
+
+def _copy_pool():
+    global _pool
+    if _pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _pool = ThreadPoolExecutor(max_workers=_COPY_THREADS, thread_name_prefix="cbas-b200-copy")
+    return _pool
+
+
 # ----------------------------------------------------------------------------------------------- encode
-def _make_pipeline(encoder, frame_hw: Tuple[int, int]):
+def _make_pipeline(encoder, frame_hw: Tuple[int, int], planes: bool = False):
     """Streaming H2D -> ViT -> D2H pipeline for one encoder/geometry (cached on the encoder object)."""
     from .pipeline import StreamedEncoder
     cache = encoder.__dict__.setdefault("_pipelines", {})
-    pipe = cache.get(frame_hw)
+    key = (tuple(frame_hw), CHUNK_SIZE, bool(planes))
+    pipe = cache.get(key)
     if pipe is None:
-        pipe = StreamedEncoder(encoder, frame_hw, CHUNK_SIZE, depth=2)
-        cache[frame_hw] = pipe
+        pipe = StreamedEncoder(encoder, frame_hw, CHUNK_SIZE, depth=2, planes=planes)
+        cache[key] = pipe
     return pipe
 
 
@@ -111,9 +189,12 @@ def encode_file(encoder, path: str, progress_callback: Optional[Callable[[float]
     if not isinstance(encoder, DinoEncoder):
         raise TypeError("cbas_b200.encode_file needs a cbas_b200.DinoEncoder (there is no PyTorch fallback path)")
     # decoder errors propagate, as in the reference (cbas.py:400-402)
-    if DECODE_WORKERS > 0 and not path.lower().endswith(".npy"):
-        from .decode import ParallelVideoReader
-        reader = ParallelVideoReader(path, workers=DECODE_WORKERS, chunk=CHUNK_SIZE)
+    # 'reference' preprocessing keeps only the green channel (cbas.py:431): decode-copy and ship that plane alone
+    green_only = encoder.preprocess == "reference"
+    if DECODE_WORKERS != 0 and not path.lower().endswith(".npy"):
+        from .decode import ParallelVideoReader, default_workers
+        reader = ParallelVideoReader(path, workers=DECODE_WORKERS if DECODE_WORKERS > 0 else default_workers(),
+                                     chunk=CHUNK_SIZE, green_only=green_only)
     else:
         reader = VideoReader(path)
     video_len = len(reader)
@@ -143,16 +224,23 @@ def encode_file(encoder, path: str, progress_callback: Optional[Callable[[float]
             writer.append(emb)  # float32 -> float16 cast on store, like dset[-n:] = embeddings_out (cbas.py:438)
             writer.flush()
 
-        it = chunks()
-        first = next(it)
-        pipe = _make_pipeline(encoder, tuple(first.shape[1:3]))
+        if hasattr(reader, "read_into") and getattr(reader, "frame_hw", None):
+            # in-thread readers: decode / copy each chunk straight into the pipeline's pinned staging, one chunk ahead
+            pipe = _make_pipeline(encoder, tuple(reader.frame_hw), planes=green_only)
+            with torch.no_grad():
+                pipe.run_reader(reader, video_len, sink, progress_callback)
+        else:
+            # the parallel decoder hands out views of its (cudaHostRegister-ed) shared-memory ring
+            it = chunks()
+            first = next(it)
+            pipe = _make_pipeline(encoder, tuple(first.shape[1:3]), planes=first.ndim == 3)
 
-        def all_chunks():
-            yield first
-            yield from it
+            def all_chunks():
+                yield first
+                yield from it
 
-        with torch.no_grad():
-            pipe.run(all_chunks(), sink)
+            with torch.no_grad():
+                pipe.run(all_chunks(), sink)
         writer.close()
         writer = None
         os.replace(tmp_file_path, out_file_path)

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 
 namespace cbas {
@@ -14,7 +15,45 @@ void set_error(const std::string& msg);
 int fail(const std::string& msg);               // set_error + return 1
 int check_cuda(cudaError_t e, const char* what);  // 0 if cudaSuccess, else records and returns 1
 void count_launch(int n = 1);
-int sm_count();
+int sm_count();  // of the calling thread's current device
+
+// Per-device "configured" state for cudaFuncSetAttribute(MaxDynamicSharedMemorySize), which is a per-DEVICE
+// attribute: one entry per device ordinal.  The value is published only after the attribute call has succeeded, so
+// a second host thread either repeats the (idempotent) call or sees it done - it never launches ahead of it.
+struct DeviceSmemOptIn {
+    std::atomic<long long> cur[64] = {};
+    template <typename Kernel>
+    cudaError_t ensure(Kernel kern, long long bytes) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        std::atomic<long long>& c = cur[dev & 63];
+        if (bytes <= c.load(std::memory_order_acquire)) return cudaSuccess;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        long long seen = c.load(std::memory_order_relaxed);
+        while (seen < bytes && !c.compare_exchange_weak(seen, bytes, std::memory_order_release)) {}
+        return cudaSuccess;
+    }
+};
+
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards: a handle created
+// on cuda:1 works from a host thread whose current device is cuda:0 (workthreads.py: one EncodeThread /
+// ClassificationThread pair per device, all in one process).
+struct DeviceGuard {
+    int prev = -1;
+    bool good = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { good = false; prev = -1; return; }
+        if (prev != device) {
+            if (cudaSetDevice(device) != cudaSuccess) { good = false; prev = -1; }
+        } else {
+            prev = -1;  // nothing to restore
+        }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    bool ok() const { return good; }
+};
 
 // Optional per-kernel timing (cbas_b200_profile_*): CUDA events recorded on the launch stream around a launch.
 enum ProfTag : int {

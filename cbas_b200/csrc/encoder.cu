@@ -1,5 +1,7 @@
-// DINOv3 ViT encoder forward on sm_100a: preprocess -> patch-embed GEMM -> L x (LN, QKV GEMM, attention with
-// RoPE prologue, proj GEMM + residual, LN, up GEMM + GELU, down GEMM + residual) -> final LN on the CLS rows.
+// DINOv3 ViT encoder forward on sm_100a: preprocess -> patch-embed GEMM -> row statistics -> L x (QKV GEMM, attention
+// with RoPE prologue, proj GEMM + residual, up GEMM + GELU, down GEMM + residual) -> final LN on the CLS rows.
+// norm1 / norm2 of every block are fused into the GEMMs around them (gemm_tcgen05.cuh: the residual GEMMs leave a
+// shifted bf16 copy of h and per-row partial sums, the QKV / up GEMMs normalise in their epilogue).
 // Reference path: cbas.py:672-677 DinoEncoder.forward -> transformers DINOv3ViTModel.forward
 // (modeling_dinov3_vit.py:530-555).  Residual stream is fp32; GEMM operands are bf16 with fp32 accumulation.
 #include "../../include/cbas_b200.h"
@@ -62,17 +64,33 @@ int launch_layernorm(const float* in, long long in_row_stride, const float* g, c
     return check_cuda(cudaGetLastError(), "layernorm_kernel launch");
 }
 
+// first link of the fused-LayerNorm chain (layernorm.cuh::ln_stats_init_kernel)
+int launch_ln_stats_init(float* h, const float* prefix_tokens, int T, int P, __nv_bfloat16* hb, float* stats, int rows,
+                         int D, cudaStream_t s) {
+    if (rows <= 0) return 0;
+    ProfScope prof(PROF_LAYERNORM, s);
+    const int threads = 256, rows_per_block = threads / 32;
+    const int grid = (rows + rows_per_block - 1) / rows_per_block;
+    switch (D) {
+        case 384: ln_stats_init_kernel<384><<<grid, threads, 0, s>>>(h, prefix_tokens, T, P, hb, stats, rows); break;
+        case 768: ln_stats_init_kernel<768><<<grid, threads, 0, s>>>(h, prefix_tokens, T, P, hb, stats, rows); break;
+        case 1024: ln_stats_init_kernel<1024><<<grid, threads, 0, s>>>(h, prefix_tokens, T, P, hb, stats, rows); break;
+        case 128: ln_stats_init_kernel<128><<<grid, threads, 0, s>>>(h, prefix_tokens, T, P, hb, stats, rows); break;
+        case 256: ln_stats_init_kernel<256><<<grid, threads, 0, s>>>(h, prefix_tokens, T, P, hb, stats, rows); break;
+        default: return fail("LayerNorm width " + std::to_string(D) + " not instantiated (128/256/384/768/1024)");
+    }
+    count_launch();
+    return check_cuda(cudaGetLastError(), "ln_stats_init_kernel launch");
+}
+
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* cs, const float* sn, int frames,
                      int T, int prefix, int heads, cudaStream_t s) {
     if (frames <= 0) return 0;
     ProfScope prof(PROF_ATTENTION, s);
     const int TP = (T + 15) & ~15;
     const int smem = 3 * TP * 128;
-    static std::atomic<int> configured_smem{0};  // two host threads may race here: the attribute call is idempotent
-    if (smem > configured_smem) {
-        CBAS_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured_smem = smem;
-    }
+    static DeviceSmemOptIn optin;  // per device (common.h)
+    CBAS_CHECK(optin.ensure(attention_kernel, smem));
     const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
     if (!cs || !sn) prefix = T;  // no rotary embedding (DINOv2): no token is a "patch token" for the rotation
     // warps per CTA: the one in 4..8 that wastes the fewest 16-row query-tile slots (ties: more warps hide more latency)
@@ -89,10 +107,11 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* 
     return check_cuda(cudaGetLastError(), "attention_kernel launch");
 }
 
-bool g_prune_last_layer = true;  // false: run the last block on every token (test knob)
-int g_resize_tiled = 2;  // test knob: 0 per-pixel kernel, 1 general tiled kernel, 2 column-per-thread kernel when it applies
-long long* g_attention_trace = nullptr;  // device buffer [64][ATC_TRACE_SLOTS] for the stage-timing aid (tools/attn_trace.py)
-int g_attention_impl = 0;  // 0 auto (tcgen05 when T <= 256), 1 mma.sync, 2 tcgen05 (both rotate q,k in their prologue)
+// Test / profiling knobs.  The encoder's own (which attention kernel, last-block pruning, which resize kernel) live in
+// the handle (cbas_b200_encoder_set_option); the two below belong to the kernel-level entry points and are per host
+// thread, so two threads never see each other's setting.
+thread_local long long* g_attention_trace = nullptr;  // device buffer [64][ATC_TRACE_SLOTS] (tools/attn_trace.py)
+thread_local int g_resize_tiled = 2;  // cbas_b200_preprocess_resize: 0 per-pixel, 1 general tiled, 2 column-per-thread
 
 bool attention_tc_fits(int T, int prefix) {
     const int TK = (T + 15) & ~15;
@@ -103,10 +122,11 @@ bool attention_tc_split_fits(int T, int prefix, bool rope) {
     const int TK = (T + 15) & ~15;
     return TK > 256 && TK <= 384 && ats_smem_bytes(TK, T, prefix, rope) <= 232448;
 }
-bool use_attention_tc(int T, int prefix, bool rope = true) {
-    if (g_attention_impl == 1) return false;
+// impl: 0 auto (tcgen05 whenever a tcgen05 kernel covers T), 1 mma.sync, 2 tcgen05
+bool use_attention_tc(int impl, int T, int prefix, bool rope = true) {
+    if (impl == 1) return false;
     if (attention_tc_split_fits(T, prefix, rope)) return true;
-    return g_attention_impl >= 2 || attention_tc_fits(T, prefix);
+    return impl >= 2 || attention_tc_fits(T, prefix);
 }
 
 // cs/sn: RoPE tables applied in the kernel's prologue, or null when q and k arrive rotated (EPI_QKV_ROPE_BF16)
@@ -131,11 +151,8 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const floa
         if (int rc = make_tmap_3d_bf16(&to, out, D, T, frames, D, 64, 128)) return rc;
         if (int rc = make_tmap_3d_bf16(&to1, out, D, T, frames, D, 64, T - 128 * (nq - 1))) return rc;
         const int smem = ats_smem_bytes(TK, T, prefix, rope);
-        static std::atomic<int> configured_split{0};
-        if (smem > configured_split) {
-            CBAS_CHECK(cudaFuncSetAttribute(attention_tc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            configured_split = smem;
-        }
+        static DeviceSmemOptIn optin_split;
+        CBAS_CHECK(optin_split.ensure(attention_tc_split_kernel, smem));
         AttnTcParams p{qkv, out, frames, heads, T, TK, D, 0.125f * 1.4426950408889634f, rope ? cs : nullptr,
                        rope ? sn : nullptr, prefix, nullptr};
         const int items = frames * heads;
@@ -159,11 +176,8 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const floa
     if (rope && (prefix < 0 || prefix >= T)) return fail("attention: bad prefix token count");
     const int smem = atc_smem_bytes(TK, T, prefix, rope);
     if (smem > 232448) return fail("attention: frame does not fit in shared memory");
-    static std::atomic<int> configured_smem{0};  // two host threads may race here: the attribute call is idempotent
-    if (smem > configured_smem) {
-        CBAS_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured_smem = smem;
-    }
+    static DeviceSmemOptIn optin;
+    CBAS_CHECK(optin.ensure(attention_tc_kernel, smem));
     AttnTcParams p{qkv, out, frames, heads, T, TK, D, 0.125f * 1.4426950408889634f, rope ? cs : nullptr,
                    rope ? sn : nullptr, prefix, g_attention_trace};
     const int items = frames * heads;
@@ -185,7 +199,7 @@ int launch_preprocess_green(const uint8_t* frames, __nv_bfloat16* A, int n, int 
 }
 
 int launch_preprocess_resize(const uint8_t* frames, __nv_bfloat16* A, int n, int H, int W, long long fs, int rs,
-                             int side, const ResizeTaps& tp, cudaStream_t s) {
+                             int side, const ResizeTaps& tp, cudaStream_t s, int resize_tiled) {
     if (n <= 0) return 0;
     if (side % 16) return fail("resize target must be a multiple of the 16-pixel patch");
     if (tp.taps_x > RESIZE_MAX_TAPS * 4 || tp.taps_y > RESIZE_MAX_TAPS * 4) return fail("too many resize taps");
@@ -199,30 +213,22 @@ int launch_preprocess_resize(const uint8_t* frames, __nv_bfloat16* A, int n, int
     const int src_pitch = (W * 3 + 15) & ~15;
     const size_t tile_smem = (size_t)max_rows * src_pitch + (size_t)max_rows * side * 3 * 4;
     const bool aligned = (reinterpret_cast<uintptr_t>(frames) & 15) == 0 && fs % 16 == 0 && rs % 16 == 0;
-    if (g_resize_tiled >= 2 && aligned && side <= 256 && tp.taps_x <= RESIZE_FAST_TAPS && tp.taps_y <= RESIZE_FAST_TAPS) {
+    if (resize_tiled >= 2 && aligned && side <= 256 && tp.taps_x <= RESIZE_FAST_TAPS && tp.taps_y <= RESIZE_FAST_TAPS) {
         // production path: column-per-thread kernel (bitwise identical to the general tiled kernel below)
         const int io_bytes = std::max(max_rows * src_pitch, (side / 16) * 1536);
         const size_t smem = (size_t)io_bytes + (size_t)3 * max_rows * side * 4 + 16 * 32 + 32;  // + row taps, + slack for the word-wise reads of the last staged row
         if (smem <= 110 * 1024) {
-            static std::atomic<size_t> configured_fast{0};
-            if (smem > configured_fast) {
-                CBAS_CHECK(cudaFuncSetAttribute(preprocess_resize_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)smem));
-                configured_fast = smem;
-            }
+            static DeviceSmemOptIn optin_fast;
+            CBAS_CHECK(optin_fast.ensure(preprocess_resize_fast_kernel, (long long)smem));
             preprocess_resize_fast_kernel<<<n * (side / 16), 256, smem, s>>>(frames, A, H, W, fs, rs, side, tp, mean, istd,
                                                                             max_rows, io_bytes);
             count_launch();
             return check_cuda(cudaGetLastError(), "preprocess_resize_fast_kernel launch");
         }
     }
-    if (g_resize_tiled && tile_smem <= 200 * 1024 && aligned) {
-        static std::atomic<size_t> configured{0};
-        if (tile_smem > configured) {
-            CBAS_CHECK(cudaFuncSetAttribute(preprocess_resize_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)tile_smem));
-            configured = tile_smem;
-        }
+    if (resize_tiled && tile_smem <= 200 * 1024 && aligned) {
+        static DeviceSmemOptIn optin_tile;
+        CBAS_CHECK(optin_tile.ensure(preprocess_resize_tile_kernel, (long long)tile_smem));
         preprocess_resize_tile_kernel<<<n * (side / 16), 256, tile_smem, s>>>(frames, A, H, W, fs, rs, side, tp, mean,
                                                                              istd, max_rows);
         count_launch();
@@ -241,22 +247,34 @@ struct cbas_encoder {
     cbas_encoder_weights w;
     std::vector<cbas_layer_weights> layers;
     int T = 0, Np = 0, Kp = 0, P = 16, ns = 0;  // tokens, patches, patch-matrix pitch, patch size, patches per side
+    int device = 0;                    // CUDA device ordinal the handle (workspace, weights) lives on
+    // per-handle test knobs (cbas_b200_encoder_set_option)
+    bool prune_last_layer = true;      // false: run the last block on every token
+    int attention_impl = 0;            // 0 auto, 1 mma.sync, 2 tcgen05
+    int resize_tiled = 2;              // 0 per-pixel kernel, 1 general tiled kernel, 2 column-per-thread kernel
     // workspace (device)
     __nv_bfloat16* a_patch = nullptr;  // [max*Np, Kp]
     float* h = nullptr;                // [max*T, D]   residual stream
-    __nv_bfloat16* xn = nullptr;       // [max*T, D]   LN output / attention output
+    __nv_bfloat16* hb = nullptr;       // [max*T, D]   bf16(h - row shift): A operand of the QKV / up GEMMs
+    float* stats[2] = {nullptr, nullptr};  // [max*T, LN_STAT_FLOATS] row statistics of h, ping-pong (proj: 0 -> 1, down: 1 -> 0)
+    __nv_bfloat16* cls_hb = nullptr;   // [max, D]  last block, CLS rows only: shifted copy after the proj update
+    float* cls_stats = nullptr;        // [max, LN_STAT_FLOATS]  ... and its statistics
+    __nv_bfloat16* xn = nullptr;       // [max*T, D]   attention output
     __nv_bfloat16* qkv = nullptr;      // [max*T, 3D]
     __nv_bfloat16* u = nullptr;        // [max*T, I]
     __nv_bfloat16* cls_q = nullptr;    // [max, D]  last block, CLS rows only: query
     __nv_bfloat16* cls_att = nullptr;  // [max, D]  attention output
-    __nv_bfloat16* cls_xn = nullptr;   // [max, D]  LN2 output
 };
 
 namespace {
 
-int encoder_embed(cbas_encoder* e, const uint8_t* frames_u8, const float* planes, int n, long long fs, int rs,
+// frames_u8 with pix == 3: interleaved RGB frames; pix == 1: one uint8 plane per frame (the green channel; REFERENCE
+// mode only).  planes: float planes in [0,1] (the DinoEncoder.__call__ contract).
+int encoder_embed(cbas_encoder* e, const uint8_t* frames_u8, int pix, const float* planes, int n, long long fs, int rs,
                   cudaStream_t s) {
     const cbas_encoder_cfg& c = e->cfg;
+    if (pix == 1 && c.mode != CBAS_PRE_REFERENCE)
+        return fail("single-plane uint8 input is only defined for REFERENCE preprocessing (green / 255)");
     if (e->P != 16) {
         // generic patch size (DINOv2-with-registers, 14 px): per-element kernels, the stage is < 3 % of the step
         ProfScope prof(PROF_PREPROCESS, s);
@@ -267,10 +285,10 @@ int encoder_embed(cbas_encoder* e, const uint8_t* frames_u8, const float* planes
             const unsigned grid = (unsigned)((total + 255) / 256);
             if (planes)
                 preprocess_green_generic_kernel<true><<<grid, 256, 0, s>>>(planes, e->a_patch, n, c.in_h, c.in_w, 0, 0,
-                                                                          e->P, e->ns, e->Kp);
+                                                                          e->P, e->ns, e->Kp, 1);
             else
                 preprocess_green_generic_kernel<false><<<grid, 256, 0, s>>>(frames_u8, e->a_patch, n, c.in_h, c.in_w, fs,
-                                                                           rs, e->P, e->ns, e->Kp);
+                                                                           rs, e->P, e->ns, e->Kp, pix);
         } else {
             ResizeTaps tp{(const int*)e->w.rs_ymin, (const float*)e->w.rs_wy, (const int*)e->w.rs_xmin,
                           (const float*)e->w.rs_wx, c.resize_taps_y, c.resize_taps_x};
@@ -288,21 +306,23 @@ int encoder_embed(cbas_encoder* e, const uint8_t* frames_u8, const float* planes
         preprocess_plane_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(planes, e->a_patch, n, c.in_h, c.in_w);
         count_launch();
         if (int rc = check_cuda(cudaGetLastError(), "preprocess_plane_kernel launch")) return rc;
+    } else if (c.mode == CBAS_PRE_REFERENCE && pix == 1) {
+        if (c.in_h % 16 || c.in_w % 16) return fail("frame size must be a multiple of the 16-pixel patch");
+        ProfScope prof(PROF_PREPROCESS, s);
+        const long long total = (long long)n * c.in_h * (c.in_w / 16);
+        preprocess_plane_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(frames_u8, e->a_patch, n, c.in_h,
+                                                                                  c.in_w, fs, rs);
+        count_launch();
+        if (int rc = check_cuda(cudaGetLastError(), "preprocess_plane_u8_kernel launch")) return rc;
     } else if (c.mode == CBAS_PRE_REFERENCE) {
         if (int rc = launch_preprocess_green(frames_u8, e->a_patch, n, c.in_h, c.in_w, fs, rs, s)) return rc;
     } else {
         ResizeTaps tp{(const int*)e->w.rs_ymin, (const float*)e->w.rs_wy, (const int*)e->w.rs_xmin,
                       (const float*)e->w.rs_wx, c.resize_taps_y, c.resize_taps_x};
-        if (int rc = launch_preprocess_resize(frames_u8, e->a_patch, n, c.in_h, c.in_w, fs, rs, c.side, tp, s)) return rc;
+        if (int rc = launch_preprocess_resize(frames_u8, e->a_patch, n, c.in_h, c.in_w, fs, rs, c.side, tp, s,
+                                              e->resize_tiled)) return rc;
     }
     const int D = c.hidden;
-    {
-        const long long total = (long long)n * c.prefix_tokens * (D / 4);
-        fill_prefix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(e->h, (const float*)e->w.prefix, n, e->T,
-                                                                          c.prefix_tokens, D);
-        count_launch();
-        if (int rc = check_cuda(cudaGetLastError(), "fill_prefix_kernel launch")) return rc;
-    }
     GemmParams p{};
     p.M = n * e->Np; p.N = D; p.K = e->Kp;
     p.bias = (const float*)e->w.b_patch;
@@ -318,66 +338,81 @@ int encoder_embed(cbas_encoder* e, const uint8_t* frames_u8, const float* planes
         add_pos_embed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(e->h, (const float*)e->w.pos_embed, n, e->T,
                                                                             c.prefix_tokens, e->Np, D);
         count_launch();
-        return check_cuda(cudaGetLastError(), "add_pos_embed_kernel launch");
+        if (int rc = check_cuda(cudaGetLastError(), "add_pos_embed_kernel launch")) return rc;
     }
-    return 0;
+    // CLS / register rows into h, then the row statistics and the shifted bf16 copy that block 0's QKV GEMM reads
+    return launch_ln_stats_init(e->h, (const float*)e->w.prefix, e->T, c.prefix_tokens, e->hb, e->stats[0], n * e->T, D, s);
+}
+
+// GemmParams of a LayerNorm-consumer GEMM (QKV, up): A is the shifted copy, bias = c2, c1 = column sums of W * gamma
+GemmParams ln_consumer(const cbas_encoder* e, int M, int N, const void* c1, const void* c2, void* out, int ldo,
+                       const float* stats, int stat_stride) {
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = e->cfg.hidden; p.bias = (const float*)c2; p.out = out; p.ldo = ldo;
+    p.ln_in = stats; p.ln_in_stride = stat_stride; p.ln_c1 = (const float*)c1;
+    p.ln_inv_dim = 1.0f / (float)e->cfg.hidden; p.ln_eps = e->cfg.ln_eps;
+    return p;
+}
+// ... and of a LayerNorm-producer GEMM (proj, down): h += A W^T + b, new shifted copy, new statistics
+GemmParams ln_producer(const cbas_encoder* e, int M, int K, const void* bias, int ldh, const float* st_in, int in_stride,
+                       float* st_out, int out_stride, __nv_bfloat16* hb, int ldhb) {
+    GemmParams p{};
+    p.M = M; p.N = e->cfg.hidden; p.K = K; p.bias = (const float*)bias; p.out = e->h; p.ldo = ldh;
+    p.ln_in = st_in; p.ln_in_stride = in_stride; p.ln_out = st_out; p.ln_out_stride = out_stride;
+    p.ln_inv_dim = 1.0f / (float)e->cfg.hidden; p.ln_eps = e->cfg.ln_eps;
+    p.hb = hb; p.ldhb = ldhb;
+    return p;
 }
 
 int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
     const cbas_encoder_cfg& c = e->cfg;
     const cbas_layer_weights& L = e->layers[li];
     const int D = c.hidden, I = c.intermediate, M = n * e->T;
-    if (int rc = launch_layernorm<__nv_bfloat16>(e->h, 1, (const float*)L.ln1_g, (const float*)L.ln1_b, e->xn, M, D,
-                                                 c.ln_eps, s)) return rc;
-    GemmParams p{};
-    p.M = M; p.N = 3 * D; p.K = D; p.bias = (const float*)L.b_qkv; p.out = e->qkv; p.ldo = 3 * D;
-    if (use_attention_tc(e->T, c.prefix_tokens, e->w.rope_cos != nullptr)) {
-        // QKV projection (V stored as f16); the tcgen05 attention kernel rotates q and k in its prologue
+    // norm1 + QKV projection (HF :433-434, :305-311)
+    GemmParams p = ln_consumer(e, M, 3 * D, L.c1_qkv, L.b_qkv, e->qkv, 3 * D, e->stats[0], 1);
+    if (use_attention_tc(e->attention_impl, e->T, c.prefix_tokens, e->w.rope_cos != nullptr)) {
+        // V stored as f16; the tcgen05 attention kernel rotates q and k in its prologue
         p.f16_from = 2 * D;
-        if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16_VF16, s, PROF_QKV_GEMM))
+        if (int rc = launch_gemm(e->hb, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16_VF16, s, PROF_QKV_GEMM))
             return rc;
         if (int rc = launch_attention_tc(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n,
                                          e->T, c.prefix_tokens, c.heads, s)) return rc;
     } else {
-        if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16, s, PROF_QKV_GEMM))
+        if (int rc = launch_gemm(e->hb, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16, s, PROF_QKV_GEMM))
             return rc;
         if (int rc = launch_attention(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n,
                                       e->T, c.prefix_tokens, c.heads, s)) return rc;
     }
-    p = GemmParams{};
-    p.M = M; p.N = D; p.K = D; p.bias = (const float*)L.b_o; p.out = e->h; p.ldo = D;
-    if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_o, D, p, EPI_RESID_F32, s, PROF_PROJ_GEMM)) return rc;
-    if (int rc = launch_layernorm<__nv_bfloat16>(e->h, 1, (const float*)L.ln2_g, (const float*)L.ln2_b, e->xn, M, D,
-                                                 c.ln_eps, s)) return rc;
-    p = GemmParams{};
-    p.M = M; p.N = I; p.K = D; p.bias = (const float*)L.b_up; p.out = e->u; p.ldo = I;
-    if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_up, D, p, EPI_BIAS_GELU_BF16, s, PROF_UP_GEMM)) return rc;
-    p = GemmParams{};
-    p.M = M; p.N = D; p.K = I; p.bias = (const float*)L.b_down; p.out = e->h; p.ldo = D;
-    return launch_gemm(e->u, I, (const __nv_bfloat16*)L.w_down, I, p, EPI_RESID_F32, s, PROF_DOWN_GEMM);
+    // output projection + LayerScale + residual (HF :440-441); leaves hb / statistics for norm2
+    p = ln_producer(e, M, D, L.b_o, D, e->stats[0], 1, e->stats[1], 1, e->hb, D);
+    if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_o, D, p, EPI_RESID_LN_F32, s, PROF_PROJ_GEMM)) return rc;
+    // norm2 + up projection + GELU (HF :445-446, :385-386)
+    p = ln_consumer(e, M, I, L.c1_up, L.b_up, e->u, I, e->stats[1], 1);
+    if (int rc = launch_gemm(e->hb, D, (const __nv_bfloat16*)L.w_up, D, p, EPI_BIAS_GELU_BF16, s, PROF_UP_GEMM)) return rc;
+    // down projection + LayerScale + residual (HF :447-448); leaves hb / statistics for the next block's norm1
+    p = ln_producer(e, M, I, L.b_down, D, e->stats[1], 1, e->stats[0], 1, e->hb, D);
+    return launch_gemm(e->u, I, (const __nv_bfloat16*)L.w_down, I, p, EPI_RESID_LN_F32, s, PROF_DOWN_GEMM);
 }
 
 // Last block, production path: the final hidden state is only read at the CLS row (HF :547-548, cbas.py:677), so
-// K and V are projected for every token but the query, attention output, proj, LN2 and the MLP run on the n CLS
+// K and V are projected for every token but the query, attention output, proj, norm2 and the MLP run on the n CLS
 // rows alone.  Mathematically identical to the full block for the row that is kept.
 int encoder_last_layer_cls_only(cbas_encoder* e, int li, int n, cudaStream_t s) {
     const cbas_encoder_cfg& c = e->cfg;
     const cbas_layer_weights& L = e->layers[li];
     const int D = c.hidden, I = c.intermediate, T = e->T, M = n * T;
-    const bool tc = use_attention_tc(T, c.prefix_tokens, e->w.rope_cos != nullptr);
-    if (int rc = launch_layernorm<__nv_bfloat16>(e->h, 1, (const float*)L.ln1_g, (const float*)L.ln1_b, e->xn, M, D,
-                                                 c.ln_eps, s)) return rc;
+    const bool tc = use_attention_tc(e->attention_impl, T, c.prefix_tokens, e->w.rope_cos != nullptr);
     const __nv_bfloat16* wqkv = (const __nv_bfloat16*)L.w_qkv;
-    const float* bqkv = (const float*)L.b_qkv;
-    GemmParams p{};
+    const float* c1 = (const float*)L.c1_qkv;
+    const float* c2 = (const float*)L.b_qkv;
     // K | V for all tokens -> columns [D, 3D) of the qkv buffer (V in the format the attention kernels expect)
-    p.M = M; p.N = 2 * D; p.K = D; p.bias = bqkv + D; p.out = e->qkv + D; p.ldo = 3 * D; p.f16_from = D;
-    if (int rc = launch_gemm(e->xn, D, wqkv + (size_t)D * D, D, p, tc ? EPI_BIAS_BF16_VF16 : EPI_BIAS_BF16, s,
+    GemmParams p = ln_consumer(e, M, 2 * D, c1 + D, c2 + D, e->qkv + D, 3 * D, e->stats[0], 1);
+    p.f16_from = D;
+    if (int rc = launch_gemm(e->hb, D, wqkv + (size_t)D * D, D, p, tc ? EPI_BIAS_BF16_VF16 : EPI_BIAS_BF16, s,
                              PROF_QKV_GEMM)) return rc;
-    // Q for the CLS rows only (A rows are T*D apart)
-    p = GemmParams{};
-    p.M = n; p.N = D; p.K = D; p.bias = bqkv; p.out = e->cls_q; p.ldo = D;
-    if (int rc = launch_gemm(e->xn, T * D, wqkv, D, p, EPI_BIAS_BF16, s, PROF_QKV_GEMM)) return rc;
+    // Q for the CLS rows only (A rows and statistics rows are T apart)
+    p = ln_consumer(e, n, D, c1, c2, e->cls_q, D, e->stats[0], T);
+    if (int rc = launch_gemm(e->hb, T * D, wqkv, D, p, EPI_BIAS_BF16, s, PROF_QKV_GEMM)) return rc;
     {
         ProfScope prof(PROF_ATTENTION, s);
         const int items = n * c.heads;
@@ -387,29 +422,28 @@ int encoder_last_layer_cls_only(cbas_encoder* e, int li, int n, cudaStream_t s) 
         count_launch();
         if (int rc = check_cuda(cudaGetLastError(), "cls_attention_kernel launch")) return rc;
     }
-    // proj + residual into the CLS rows of h (output rows are T*D apart)
-    p = GemmParams{};
-    p.M = n; p.N = D; p.K = D; p.bias = (const float*)L.b_o; p.out = e->h; p.ldo = T * D;
-    if (int rc = launch_gemm(e->cls_att, D, (const __nv_bfloat16*)L.w_o, D, p, EPI_RESID_F32, s, PROF_PROJ_GEMM)) return rc;
-    if (int rc = launch_layernorm<__nv_bfloat16>(e->h, T, (const float*)L.ln2_g, (const float*)L.ln2_b, e->cls_xn, n, D,
-                                                 c.ln_eps, s)) return rc;
-    p = GemmParams{};
-    p.M = n; p.N = I; p.K = D; p.bias = (const float*)L.b_up; p.out = e->u; p.ldo = I;
-    if (int rc = launch_gemm(e->cls_xn, D, (const __nv_bfloat16*)L.w_up, D, p, EPI_BIAS_GELU_BF16, s, PROF_UP_GEMM)) return rc;
+    // proj + residual into the CLS rows of h (rows T*D apart); compact shifted copy and statistics for norm2
+    p = ln_producer(e, n, D, L.b_o, T * D, e->stats[0], T, e->cls_stats, 1, e->cls_hb, D);
+    if (int rc = launch_gemm(e->cls_att, D, (const __nv_bfloat16*)L.w_o, D, p, EPI_RESID_LN_F32, s, PROF_PROJ_GEMM)) return rc;
+    p = ln_consumer(e, n, I, L.c1_up, L.b_up, e->u, I, e->cls_stats, 1);
+    if (int rc = launch_gemm(e->cls_hb, D, (const __nv_bfloat16*)L.w_up, D, p, EPI_BIAS_GELU_BF16, s, PROF_UP_GEMM)) return rc;
+    // nothing normalises this output inside the block (the final norm reads h itself): plain residual update
     p = GemmParams{};
     p.M = n; p.N = D; p.K = I; p.bias = (const float*)L.b_down; p.out = e->h; p.ldo = T * D;
     return launch_gemm(e->u, I, (const __nv_bfloat16*)L.w_down, I, p, EPI_RESID_F32, s, PROF_DOWN_GEMM);
 }
 
-int encoder_forward(cbas_encoder* e, const uint8_t* frames_u8, const float* planes, int n, long long fs, int rs,
+int encoder_forward(cbas_encoder* e, const uint8_t* frames_u8, int pix, const float* planes, int n, long long fs, int rs,
                     int stop_after_layer, float* hidden_out, float* emb_out, cudaStream_t s) {
     if (!e) return fail("null encoder");
+    DeviceGuard guard(e->device);  // the handle's device, whatever the calling thread's current device is
+    if (!guard.ok()) return fail("cudaSetDevice to the encoder's device failed");
     if (n < 0 || n > e->cfg.max_frames) return fail("n exceeds the encoder's max_frames");
     if (n == 0) return 0;
-    if (int rc = encoder_embed(e, frames_u8, planes, n, fs, rs, s)) return rc;
+    if (int rc = encoder_embed(e, frames_u8, pix, planes, n, fs, rs, s)) return rc;
     const int L = stop_after_layer >= 0 ? stop_after_layer : e->cfg.layers;
     // only the pooled CLS embedding is wanted: the last block can skip every row that is thrown away
-    const bool prune = g_prune_last_layer && stop_after_layer < 0 && !hidden_out && e->T <= CLS_ATT_MAX_T && L >= 1;
+    const bool prune = e->prune_last_layer && stop_after_layer < 0 && !hidden_out && e->T <= CLS_ATT_MAX_T && L >= 1;
     for (int li = 0; li < L; ++li) {
         if (prune && li == L - 1) {
             if (int rc = encoder_last_layer_cls_only(e, li, n, s)) return rc;
@@ -446,6 +480,7 @@ int cbas_b200_encoder_create(const cbas_encoder_cfg* cfg, const cbas_encoder_wei
     if (cfg->mode != CBAS_PRE_REFERENCE && cfg->mode != CBAS_PRE_PROCESSOR) return fail("unknown preprocessing mode");
     if (cfg->max_frames <= 0) return fail("max_frames must be positive");
     auto* e = new cbas_encoder();
+    CBAS_CHECK(cudaGetDevice(&e->device));  // the handle belongs to the device that is current at create time
     e->cfg = *cfg;
     e->w = *w;
     e->layers.assign(w->layers, w->layers + cfg->layers);
@@ -466,12 +501,20 @@ int cbas_b200_encoder_create(const cbas_encoder_cfg* cfg, const cbas_encoder_wei
     if (err == cudaSuccess && P != 16)  // the padding columns of the patch matrix stay zero for the handle's lifetime
         err = cudaMemset(e->a_patch, 0, (size_t)cfg->max_frames * e->Np * e->Kp * 2);
     alloc((void**)&e->h, mt * D * 4);
+    alloc((void**)&e->hb, mt * D * 2);
+    for (int i = 0; i < 2; ++i) {
+        // slots no GEMM of this geometry writes must read as zero for the handle's lifetime
+        alloc((void**)&e->stats[i], mt * LN_STAT_FLOATS * 4);
+        if (err == cudaSuccess) err = cudaMemset(e->stats[i], 0, mt * LN_STAT_FLOATS * 4);
+    }
+    alloc((void**)&e->cls_hb, (size_t)cfg->max_frames * D * 2);
+    alloc((void**)&e->cls_stats, (size_t)cfg->max_frames * LN_STAT_FLOATS * 4);
+    if (err == cudaSuccess) err = cudaMemset(e->cls_stats, 0, (size_t)cfg->max_frames * LN_STAT_FLOATS * 4);
     alloc((void**)&e->xn, mt * D * 2);
     alloc((void**)&e->qkv, mt * 3 * D * 2);
     alloc((void**)&e->u, mt * (size_t)cfg->intermediate * 2);
     alloc((void**)&e->cls_q, (size_t)cfg->max_frames * D * 2);
     alloc((void**)&e->cls_att, (size_t)cfg->max_frames * D * 2);
-    alloc((void**)&e->cls_xn, (size_t)cfg->max_frames * D * 2);
     if (err != cudaSuccess) {
         cbas_b200_encoder_destroy(e);
         return check_cuda(err, "encoder workspace cudaMalloc");
@@ -482,27 +525,35 @@ int cbas_b200_encoder_create(const cbas_encoder_cfg* cfg, const cbas_encoder_wei
 
 void cbas_b200_encoder_destroy(cbas_encoder* e) {
     if (!e) return;
+    DeviceGuard guard(e->device);
     cudaFree(e->a_patch); cudaFree(e->h); cudaFree(e->xn); cudaFree(e->qkv); cudaFree(e->u);
-    cudaFree(e->cls_q); cudaFree(e->cls_att); cudaFree(e->cls_xn);
+    cudaFree(e->hb); cudaFree(e->stats[0]); cudaFree(e->stats[1]); cudaFree(e->cls_hb); cudaFree(e->cls_stats);
+    cudaFree(e->cls_q); cudaFree(e->cls_att);
     delete e;
 }
 
 int cbas_b200_encoder_forward_u8(cbas_encoder* enc, const uint8_t* frames_dev, int32_t n, int64_t frame_stride,
                                  int32_t row_stride, float* emb_out_dev, void* stream) {
-    return encoder_forward(enc, frames_dev, nullptr, n, frame_stride, row_stride, -1, nullptr, emb_out_dev,
+    return encoder_forward(enc, frames_dev, 3, nullptr, n, frame_stride, row_stride, -1, nullptr, emb_out_dev,
+                           (cudaStream_t)stream);
+}
+
+int cbas_b200_encoder_forward_u8_plane(cbas_encoder* enc, const uint8_t* planes_dev, int32_t n, int64_t frame_stride,
+                                       int32_t row_stride, float* emb_out_dev, void* stream) {
+    return encoder_forward(enc, planes_dev, 1, nullptr, n, frame_stride, row_stride, -1, nullptr, emb_out_dev,
                            (cudaStream_t)stream);
 }
 
 int cbas_b200_encoder_forward_f32(cbas_encoder* enc, const float* planes_dev, int32_t n, float* emb_out_dev,
                                   void* stream) {
-    return encoder_forward(enc, nullptr, planes_dev, n, 0, 0, -1, nullptr, emb_out_dev, (cudaStream_t)stream);
+    return encoder_forward(enc, nullptr, 3, planes_dev, n, 0, 0, -1, nullptr, emb_out_dev, (cudaStream_t)stream);
 }
 
 int cbas_b200_encoder_debug_hidden(cbas_encoder* enc, const uint8_t* frames_dev, int32_t n, int64_t frame_stride,
                                    int32_t row_stride, int32_t after_layer, float* hidden_out_dev, void* stream) {
     if (!enc) return fail("null encoder");
     if (after_layer < 0 || after_layer > enc->cfg.layers) return fail("after_layer out of range");
-    return encoder_forward(enc, frames_dev, nullptr, n, frame_stride, row_stride, after_layer, hidden_out_dev, nullptr,
+    return encoder_forward(enc, frames_dev, 3, nullptr, n, frame_stride, row_stride, after_layer, hidden_out_dev, nullptr,
                            (cudaStream_t)stream);
 }
 
@@ -514,10 +565,17 @@ int cbas_b200_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_
     return launch_gemm((const __nv_bfloat16*)a_dev, K, (const __nv_bfloat16*)w_dev, K, p, epi, (cudaStream_t)stream);
 }
 
-int cbas_b200_debug_attention_impl(int32_t impl) {
-    if (impl < 0 || impl > 2) return fail("attention impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
-    g_attention_impl = impl;
-    return 0;
+int cbas_b200_encoder_set_option(cbas_encoder* enc, int32_t option, int32_t value) {
+    if (!enc) return fail("null encoder");
+    switch (option) {
+        case CBAS_OPT_ATTENTION_IMPL:
+            if (value < 0 || value > 2) return fail("attention impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
+            enc->attention_impl = value;
+            return 0;
+        case CBAS_OPT_PRUNE_LAST_LAYER: enc->prune_last_layer = value != 0; return 0;
+        case CBAS_OPT_RESIZE_KERNEL: enc->resize_tiled = value < 0 ? 0 : (value > 2 ? 2 : value); return 0;
+    }
+    return fail("unknown encoder option " + std::to_string(option));
 }
 
 int cbas_b200_attention_tc(const void* qkv_bf16_dev, void* out_bf16_dev, const float* rope_cos_dev,
@@ -529,11 +587,6 @@ int cbas_b200_attention_tc(const void* qkv_bf16_dev, void* out_bf16_dev, const f
 
 int cbas_b200_debug_attention_trace(void* trace_dev) {
     g_attention_trace = (long long*)trace_dev;
-    return 0;
-}
-
-int cbas_b200_debug_prune_last_layer(int32_t on) {
-    g_prune_last_layer = on != 0;
     return 0;
 }
 
@@ -552,6 +605,35 @@ int cbas_b200_layernorm(const float* in_dev, const float* gamma_dev, const float
                         int32_t rows, int32_t D, float eps, void* stream) {
     return launch_layernorm<__nv_bfloat16>(in_dev, 1, gamma_dev, beta_dev, (__nv_bfloat16*)out_bf16_dev, rows, D, eps,
                                            (cudaStream_t)stream);
+}
+
+int cbas_b200_ln_stats_init(float* h_dev, void* hb_out_dev, float* stats_out_dev, int32_t rows, int32_t D,
+                            void* stream) {
+    return launch_ln_stats_init(h_dev, nullptr, 1, 0, (__nv_bfloat16*)hb_out_dev, stats_out_dev, rows, D,
+                                (cudaStream_t)stream);
+}
+
+int cbas_b200_gemm_resid_ln(const void* a_dev, const void* w_dev, const float* bias_dev, float* h_dev, void* hb_out_dev,
+                            const float* stats_in_dev, float* stats_out_dev, int32_t M, int32_t N, int32_t K,
+                            void* stream) {
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.bias = bias_dev; p.out = h_dev; p.ldo = N;
+    p.ln_in = stats_in_dev; p.ln_in_stride = 1; p.ln_out = stats_out_dev; p.ln_out_stride = 1;
+    p.ln_inv_dim = 1.0f / (float)N; p.hb = hb_out_dev; p.ldhb = N;
+    return launch_gemm((const __nv_bfloat16*)a_dev, K, (const __nv_bfloat16*)w_dev, K, p, EPI_RESID_LN_F32,
+                       (cudaStream_t)stream);
+}
+
+int cbas_b200_gemm_ln_a(const void* hb_dev, const float* stats_dev, const void* w_folded_dev, const float* c1_dev,
+                        const float* c2_dev, void* out_bf16_dev, int32_t M, int32_t N, int32_t K, int32_t epi,
+                        float eps, void* stream) {
+    if (epi != EPI_BIAS_BF16 && epi != EPI_BIAS_GELU_BF16) return fail("LayerNorm-consumer GEMM: epi must be 0 or 1");
+    if (!stats_dev) return fail("LayerNorm-consumer GEMM needs the row statistics");
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.bias = c2_dev; p.out = out_bf16_dev; p.ldo = N;
+    p.ln_in = stats_dev; p.ln_in_stride = 1; p.ln_c1 = c1_dev; p.ln_inv_dim = 1.0f / (float)K; p.ln_eps = eps;
+    return launch_gemm((const __nv_bfloat16*)hb_dev, K, (const __nv_bfloat16*)w_folded_dev, K, p, epi,
+                       (cudaStream_t)stream);
 }
 
 int cbas_b200_attention_tc_supported(int32_t T, int32_t prefix, int32_t rope) {
@@ -579,7 +661,7 @@ int cbas_b200_preprocess_resize(const uint8_t* frames_dev, void* a_bf16_dev, int
                                 int32_t taps_x, void* stream) {
     ResizeTaps tp{ymin_dev, wy_dev, xmin_dev, wx_dev, taps_y, taps_x};
     return launch_preprocess_resize(frames_dev, (__nv_bfloat16*)a_bf16_dev, n, H, W, frame_stride, row_stride, side,
-                                    tp, (cudaStream_t)stream);
+                                    tp, (cudaStream_t)stream, g_resize_tiled);
 }
 
 }  // extern "C"

@@ -11,7 +11,7 @@ namespace cbas {
 
 namespace {
 
-int g_force_cg = 0;  // 0 = automatic; 1 / 2 force the CTA-group size (tests, A/B timing)
+thread_local int g_force_cg = 0;  // 0 = automatic; 1 / 2 force the CTA-group size (tests, A/B timing); per host thread
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -50,14 +50,21 @@ int make_tmap(CUtensorMap* map, const void* base, bool f32, int rows, int cols, 
 
 template <int BLOCK_N, int EPI, int CG>
 int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-    using Cfg = GemmCfg<BLOCK_N, CG, gemm_epi_double_stage(EPI)>;
+    using Cfg = GemmCfg<BLOCK_N, CG, gemm_epi_double_stage(EPI), gemm_epi_ln_producer(EPI) ? gemm_ln_bufs(EPI) : 0>;
     auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI, CG>;
-    static std::atomic<bool> configured{false};  // per instantiation; a race between host threads only repeats the call
-    if (!configured) {
-        CBAS_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        configured = true;
-    }
+    // the opt-in is a per-DEVICE attribute: one flag per instantiation and device ordinal
+    static DeviceSmemOptIn optin;
+    CBAS_CHECK(optin.ensure(kern, Cfg::kSmemBytes));
     CUtensorMap tout = ta;  // unused by the direct-store (patch) epilogue
+    if (gemm_epi_ln_producer(EPI)) {
+        if (!p.ln_in || !p.ln_out || !p.hb) return fail("LayerNorm-producer GEMM needs statistics in/out and the bf16 copy");
+        if (4 * (p.N / BLOCK_N) > LN_STAT_SLOTS) return fail("LayerNorm-producer GEMM: N too wide for the statistics slots");
+        if ((reinterpret_cast<uintptr_t>(p.hb) & 31) || (p.ldhb % 16) || (reinterpret_cast<uintptr_t>(p.ln_in) & 15))
+            return fail("LayerNorm-producer GEMM: hb must be 32-byte aligned (row pitch too), statistics 16-byte aligned");
+    } else if (gemm_epi_out_bf16(EPI) && p.ln_in) {
+        if (!p.ln_c1 || !p.bias) return fail("LayerNorm-consumer GEMM needs c1 and c2");
+        if (reinterpret_cast<uintptr_t>(p.ln_in) & 15) return fail("LayerNorm statistics must be 16-byte aligned");
+    }
     if (gemm_epi_staged(EPI)) {
         const bool f32 = !gemm_epi_out_bf16(EPI);
         if ((reinterpret_cast<uintptr_t>(p.out) & 15) || (p.ldo % (f32 ? 4 : 8)))
@@ -100,6 +107,11 @@ int launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
         case EPI_BIAS_F32: return launch_one<BLOCK_N, EPI_BIAS_F32, CG>(ta, tb, p, stream);
         case EPI_BIAS_GELU_F32: return launch_one<BLOCK_N, EPI_BIAS_GELU_F32, CG>(ta, tb, p, stream);
         case EPI_BIAS_BF16_VF16: return launch_one<BLOCK_N, EPI_BIAS_BF16_VF16, CG>(ta, tb, p, stream);
+        // long mainloop: one old-h slab buffer per epilogue group and a deeper operand ring; short: prefetched slabs
+        case EPI_RESID_LN_F32:
+        case EPI_RESID_LN1_F32:
+            if (p.K > 1536) return launch_one<BLOCK_N, EPI_RESID_LN1_F32, CG>(ta, tb, p, stream);
+            return launch_one<BLOCK_N, EPI_RESID_LN_F32, CG>(ta, tb, p, stream);
     }
     return fail("unknown GEMM epilogue " + std::to_string(epi));
 }

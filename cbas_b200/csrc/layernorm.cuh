@@ -54,4 +54,51 @@ layernorm_kernel(const float* __restrict__ in, long long in_row_stride, const fl
     }
 }
 
+// Start of the fused-LayerNorm chain (gemm_tcgen05.cuh header): exact two-pass statistics of every row of the freshly
+// embedded residual stream, the shifted bf16 copy hb = bf16(h - mean) the first QKV GEMM reads as its A operand, and
+// the statistics row {sum y = 0, sum y^2 = sum (x - mean)^2, shift = mean}.  Rows of the CLS / register prefix are
+// taken from the token table and written into h here (HF modeling_dinov3_vit.py:85-90: cat(cls, registers, patches)),
+// so the embedding stage needs no separate fill kernel.  One launch per forward pass; HBM-bound like layernorm_kernel.
+//   h: [rows, D] fp32, row = frame * T + token;  prefix_tokens: [P, D] or null (then every row is read from h)
+template <int D>
+__global__ void __launch_bounds__(256)
+ln_stats_init_kernel(float* __restrict__ h, const float* __restrict__ prefix_tokens, int T, int P,
+                     __nv_bfloat16* __restrict__ hb, float* __restrict__ stats, int rows) {
+    static_assert(D % 128 == 0, "D must be a multiple of 128");
+    constexpr int V = D / 128;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float4* hrow = reinterpret_cast<float4*>(h + (long long)row * D);
+    const int token = prefix_tokens ? row % T : P;
+    float4 x[V];
+    if (token < P) {
+        const float4* src = reinterpret_cast<const float4*>(prefix_tokens + (long long)token * D);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { x[i] = __ldg(src + lane + 32 * i); hrow[lane + 32 * i] = x[i]; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) x[i] = hrow[lane + 32 * i];
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        x[i].x -= mean; x[i].y -= mean; x[i].z -= mean; x[i].w -= mean;
+        q += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
+        uint2 o;
+        o.x = pack_bf16(x[i].x, x[i].y);
+        o.y = pack_bf16(x[i].z, x[i].w);
+        reinterpret_cast<uint2*>(hb + (long long)row * D)[lane + 32 * i] = o;
+    }
+    q = warp_sum(q);
+    // LN_STAT_FLOATS = 36 floats per row (gemm_tcgen05.cuh): sums[16] = 0, squares[16] = {q, 0...}, shift, padding
+    float* srow = stats + (long long)row * 36;
+    srow[lane] = lane == 16 ? q : 0.f;
+    if (lane < 4) srow[32 + lane] = lane == 0 ? mean : 0.f;
+}
+
 }  // namespace cbas

@@ -59,6 +59,39 @@ preprocess_green_kernel(const uint8_t* __restrict__ frames, __nv_bfloat16* __res
     reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
+// The same for a frame that arrives as ONE uint8 plane [H, W] (the decode workers ship only the green plane in
+// REFERENCE mode: a third of the host-to-device bytes): 16 contiguous bytes -> 16 bf16.
+__global__ void __launch_bounds__(256)
+preprocess_plane_u8_kernel(const uint8_t* __restrict__ planes, __nv_bfloat16* __restrict__ A, int n_frames, int H,
+                           int W, long long frame_stride, int row_stride) {
+    const int nw = W >> 4, nh = H >> 4;
+    const long long total = (long long)n_frames * H * nw;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int px = gid % nw;
+    const long long t = gid / nw;
+    const int y = t % H;
+    const int f = t / H;
+    const uint8_t* src = planes + f * frame_stride + (long long)y * row_stride + px * 16;
+    uint32_t w[4];
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            w[i] = src[4 * i] | (src[4 * i + 1] << 8) | (src[4 * i + 2] << 16) | (uint32_t(src[4 * i + 3]) << 24);
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2)
+        o[i >> 1] = pack_bf16(float((w[i >> 2] >> ((i & 3) * 8)) & 0xff), float((w[(i + 1) >> 2] >> (((i + 1) & 3) * 8)) & 0xff));
+    const int py = y >> 4, ky = y & 15;
+    __nv_bfloat16* dst = A + ((long long)f * nh * nw + (long long)py * nw + px) * 256 + ky * 16;
+    reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
 constexpr int RESIZE_MAX_TAPS = 8;
 
 struct ResizeTaps {
@@ -347,7 +380,7 @@ fill_prefix_kernel(float* __restrict__ h, const float* __restrict__ prefix_token
 template <bool PLANE>
 __global__ void __launch_bounds__(256)
 preprocess_green_generic_kernel(const void* __restrict__ src, __nv_bfloat16* __restrict__ A, int n_frames, int H, int W,
-                                long long frame_stride, int row_stride, int P, int ns, int Kp) {
+                                long long frame_stride, int row_stride, int P, int ns, int Kp, int pix_stride) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)n_frames * ns * P * ns;
     if (idx >= total) return;
@@ -362,9 +395,10 @@ preprocess_green_generic_kernel(const void* __restrict__ src, __nv_bfloat16* __r
         const float* g = reinterpret_cast<const float*>(src) + ((long long)f * H + y) * W + x0;
         for (int kx = 0; kx < P; ++kx) dst[kx] = __float2bfloat16_rn(g[kx] * 255.0f);
     } else {
+        // pix_stride 3: interleaved RGB, take green; 1: the frame IS the green plane
         const uint8_t* g = reinterpret_cast<const uint8_t*>(src) + (long long)f * frame_stride + (long long)y * row_stride +
-                           x0 * 3 + 1;  // green
-        for (int kx = 0; kx < P; ++kx) dst[kx] = __float2bfloat16_rn((float)g[3 * kx]);
+                           x0 * pix_stride + (pix_stride == 3 ? 1 : 0);
+        for (int kx = 0; kx < P; ++kx) dst[kx] = __float2bfloat16_rn((float)g[pix_stride * kx]);
     }
 }
 

@@ -340,6 +340,16 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
     return __bfloat1622float2(v);
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* ptr) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+}
+// 32-byte global store (sm_100: STG.256): one full sector per thread; `ptr` must be 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

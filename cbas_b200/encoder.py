@@ -192,6 +192,34 @@ def interpolate_pos_embed(pos: torch.Tensor, n_h: int, n_w: int) -> Tuple[torch.
     return cls_pos, grid.permute(0, 2, 3, 1).reshape(n_h * n_w, D)
 
 
+def fold_layernorm(w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+    """LayerNorm(gamma, beta) followed by Linear(w, b), rewritten for the fused kernels (csrc/gemm_tcgen05.cuh):
+    LN(h) W^T + b = rstd * (h - mean) W'^T + c2 with W' = W * gamma.  Returns (W' as bf16, c1, c2) where
+    c1[n] = sum_k W'[n,k] is taken over the bf16-ROUNDED W' (it must cancel the tensor-core sum exactly when a row of
+    h is constant) and c2 = W beta + b; sums in float64."""
+    w64, g64 = w.double(), gamma.double()
+    w_folded = (w64 * g64[None, :]).to(torch.bfloat16)
+    c1 = w_folded.double().sum(dim=1).float()
+    c2 = (w64 @ beta.double() + b.double()).float()
+    return w_folded, c1, c2
+
+
+def normalize_dinov3_keys(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """transformers 5.x names the DINOv3 blocks `model.layer.{i}.*`; the 4.5x releases the reference's
+    requirements.txt also admits (`transformers>=4.53.3`) use `layer.{i}.*`.  Accept both (and an optional leading
+    `model.` from a wrapping module) and return the 5.x layout the packer reads."""
+    if any(k.startswith("model.layer.") for k in sd):
+        return sd
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("model.embeddings.") or k.startswith("model.norm.") or k.startswith("model.model.layer."):
+            k = k[len("model."):]
+        if k.startswith("layer."):
+            k = "model." + k
+        out[k] = v
+    return out
+
+
 class _NativeEncoder:
     """One libcbas_b200 encoder handle for a fixed input geometry; owns the device weight tensors."""
 
@@ -209,7 +237,7 @@ class _NativeEncoder:
             return t.data_ptr()
 
         f32, bf16 = torch.float32, torch.bfloat16
-        sd = normalize_state_dict(sd, cfg.family)
+        sd = normalize_dinov3_keys(normalize_state_dict(sd, cfg.family))
         P = cfg.patch_size
         wp = sd["embeddings.patch_embeddings.weight"].float()
         if mode == PRE_REFERENCE:
@@ -230,27 +258,33 @@ class _NativeEncoder:
         else:
             cos, sin = rope_tables(n_side, n_side, D // cfg.num_attention_heads, cfg.rope_theta)
 
+        I = cfg.intermediate_size
+
+        def opt(key: str, n: int) -> torch.Tensor:
+            # the HF configs allow query_bias / value_bias / proj_bias / mlp_bias = False: an absent bias is zero
+            t = sd.get(key)
+            return t.float() if t is not None else torch.zeros(n)
+
         layers = (_lib.LayerWeights * cfg.num_hidden_layers)()
         for i in range(cfg.num_hidden_layers):
             p = f"model.layer.{i}."
             q_w, k_w, v_w = (sd[p + f"attention.{n}_proj.weight"].float() for n in "qkv")
-            q_b = sd[p + "attention.q_proj.bias"].float()
-            v_b = sd[p + "attention.v_proj.bias"].float()
-            k_b = sd.get(p + "attention.k_proj.bias")
-            k_b = k_b.float() if k_b is not None else torch.zeros(D)  # key_bias=False in DINOv3
+            qkv_b = torch.cat([opt(p + f"attention.{n}_proj.bias", D) for n in "qkv"])  # key_bias=False in DINOv3
             l1 = sd[p + "layer_scale1.lambda1"].float()
             l2 = sd[p + "layer_scale2.lambda1"].float()
             lw = layers[i]
-            lw.ln1_g, lw.ln1_b = dev(sd[p + "norm1.weight"], f32), dev(sd[p + "norm1.bias"], f32)
-            lw.ln2_g, lw.ln2_b = dev(sd[p + "norm2.weight"], f32), dev(sd[p + "norm2.bias"], f32)
-            lw.w_qkv = dev(torch.cat([q_w, k_w, v_w], dim=0), bf16)
-            lw.b_qkv = dev(torch.cat([q_b, k_b, v_b], dim=0), f32)
+            # norm1 / norm2 (modeling_dinov3_vit.py:433,445) folded into the projection behind them
+            wq, c1, c2 = fold_layernorm(torch.cat([q_w, k_w, v_w], dim=0), qkv_b,
+                                        sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+            lw.w_qkv, lw.c1_qkv, lw.b_qkv = dev(wq, bf16), dev(c1, f32), dev(c2, f32)
+            wu, c1, c2 = fold_layernorm(sd[p + "mlp.up_proj.weight"], opt(p + "mlp.up_proj.bias", I),
+                                        sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+            lw.w_up, lw.c1_up, lw.b_up = dev(wu, bf16), dev(c1, f32), dev(c2, f32)
             # LayerScale (modeling_dinov3_vit.py:337-343) folded into the projection that feeds it
             lw.w_o = dev(sd[p + "attention.o_proj.weight"].float() * l1[:, None], bf16)
-            lw.b_o = dev(sd[p + "attention.o_proj.bias"].float() * l1, f32)
-            lw.w_up, lw.b_up = dev(sd[p + "mlp.up_proj.weight"], bf16), dev(sd[p + "mlp.up_proj.bias"], f32)
+            lw.b_o = dev(opt(p + "attention.o_proj.bias", D) * l1, f32)
             lw.w_down = dev(sd[p + "mlp.down_proj.weight"].float() * l2[:, None], bf16)
-            lw.b_down = dev(sd[p + "mlp.down_proj.bias"].float() * l2, f32)
+            lw.b_down = dev(opt(p + "mlp.down_proj.bias", D) * l2, f32)
         self._layers = layers
 
         w = _lib.EncoderWeights()
@@ -277,6 +311,9 @@ class _NativeEncoder:
             _lib.check(self.lib.cbas_b200_encoder_create(C.byref(c), C.byref(w), C.byref(handle)), "encoder_create")
         self.handle = handle
         self.tokens = n_side * n_side + 1 + cfg.num_register_tokens
+
+    def set_option(self, option: int, value: int) -> None:
+        _lib.check(self.lib.cbas_b200_encoder_set_option(self.handle, option, value), "encoder_set_option")
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -337,6 +374,7 @@ class DinoEncoder(nn.Module):
         self._sd = {k: v.detach().cpu() for k, v in sd.items()}
         self.hidden_size = self.config.hidden_size
         self._native: Dict[Tuple[int, int, int], _NativeEncoder] = {}
+        self._options: Dict[int, int] = {}
         self.eval()
 
     # -- construction helpers -------------------------------------------------------------------------
@@ -353,8 +391,17 @@ class DinoEncoder(nn.Module):
             if mode == PRE_REFERENCE and in_hw[0] != in_hw[1]:
                 raise ValueError("reference preprocessing expects square frames (cbas.py:768-784 records square clips)")
             nat = _NativeEncoder(self.config, self._sd, self.device, mode, in_hw, side, self.max_frames)
+            for opt, val in self._options.items():
+                nat.set_option(opt, val)
             self._native[key] = nat
         return nat
+
+    def set_option(self, option: int, value: int) -> None:
+        """Test knob of this encoder (cbas_b200_encoder_set_option: _lib.OPT_ATTENTION_IMPL / OPT_PRUNE_LAST_LAYER /
+        OPT_RESIZE_KERNEL); applies to the handles of every geometry, present and future."""
+        self._options[option] = int(value)
+        for nat in self._native.values():
+            nat.set_option(option, int(value))
 
     # -- reference-compatible call ---------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -390,6 +437,28 @@ class DinoEncoder(nn.Module):
             _lib.check(nat.lib.cbas_b200_encoder_forward_u8(
                 nat.handle, frames[i:i + m].data_ptr(), m, H * W * 3, W * 3, out[i:i + m].data_ptr(), stream),
                 "encoder_forward_u8")
+        return out
+
+    def encode_u8_plane(self, planes: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """planes: uint8 [n,H,W] on self.device, the green channel of each frame (what cbas.py:431 keeps) ->
+        [n,D] fp32 CLS embeddings; 'reference' preprocessing only.  Same result as encode_u8 on the RGB frames."""
+        if planes.dtype != torch.uint8 or planes.dim() != 3:
+            raise ValueError("encode_u8_plane expects uint8 [n,H,W]")
+        if self.preprocess != "reference":
+            raise ValueError("single-plane input is only defined for preprocess='reference' (green / 255)")
+        if planes.device != self.device:
+            raise ValueError("encode_u8_plane expects planes already on the encoder's device")
+        planes = planes.contiguous()
+        n, H, W = planes.shape
+        nat = self._get_native(PRE_REFERENCE, (H, W))
+        if out is None:
+            out = torch.empty(n, self.hidden_size, device=self.device, dtype=torch.float32)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for i in range(0, n, nat.max_frames):
+            m = min(nat.max_frames, n - i)
+            _lib.check(nat.lib.cbas_b200_encoder_forward_u8_plane(
+                nat.handle, planes[i:i + m].data_ptr(), m, H * W, W, out[i:i + m].data_ptr(), stream),
+                "encoder_forward_u8_plane")
         return out
 
     def debug_hidden(self, frames: torch.Tensor, after_layer: int) -> torch.Tensor:

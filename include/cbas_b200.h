@@ -10,6 +10,10 @@
  * non-zero on failure; cbas_b200_last_error() returns a thread-local message for the last failure.
  * The library is re-entrant across host threads as long as two threads do not share one Encoder/Head handle
  * (workthreads.py:272,370 - one EncodeThread and one ClassificationThread, each on its own CUDA stream).
+ * A handle belongs to the CUDA device that was current when it was created; every call on the handle makes that
+ * device current for its duration and restores the caller's, so one process can drive several GPUs from several
+ * threads (workthreads.py:267-272,1245-1273).  The kernel-level entry points (no handle) run on the calling thread's
+ * current device.  Test knobs are either per handle (cbas_b200_encoder_set_option) or per host thread.
  */
 #ifndef CBAS_B200_H
 #define CBAS_B200_H
@@ -20,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CBAS_B200_ABI_VERSION 2
+#define CBAS_B200_ABI_VERSION 3
 
 /* preprocessing modes (SURVEY.md 8a rows P / P') */
 #define CBAS_PRE_REFERENCE 0 /* cbas.py:431 + cbas.py:672-675: green/255 replicated x3, native resolution   */
@@ -34,6 +38,7 @@ unsigned long long cbas_b200_launch_count(void);
 /* Per-kernel device timing for bench.py's roofline leg: while enabled, every launch is bracketed by CUDA events
  * on its own stream (tags: 0 preprocess, 1 patch GEMM, 2 LayerNorm, 3 QKV GEMM, 4 attention, 5 proj GEMM,
  * 6 up GEMM(+GELU), 7 down GEMM, 8 final LN, 9.. head stages, 16 actogram, 17 other).  enable(1) also clears.
+ * Tag 2 counts the one statistics pass after the embedding: norm1 / norm2 themselves are fused into the GEMMs.
  * profile_read synchronises on the recorded events and returns the summed duration and launch count of a tag. */
 int cbas_b200_profile_enable(int on);
 int cbas_b200_profile_read(int tag, double* total_ms, long long* launches);
@@ -58,12 +63,15 @@ typedef struct {
                               floor(side / patch) patches per side, like the stride-`patch` Conv2d it replaces        */
 } cbas_encoder_cfg;
 
+/* norm1 / norm2 (modeling_dinov3_vit.py:433,445) are fused into the GEMMs around them (csrc/gemm_tcgen05.cuh): the
+ * host folds gamma into the weight that follows the norm, W' = W * gamma (per input column), and passes
+ *   c1[n] = sum_k W'[n,k]  (of the bf16-rounded W'),   c2[n] = sum_k W[n,k] * beta[k] + bias[n]
+ * so that  LN(h) W^T + bias = rstd * (h - mean) W'^T + c2 = rstd * ((h - s) W'^T) - rstd * (mean - s) * c1 + c2. */
 typedef struct {
-    const void* ln1_g; const void* ln1_b;     /* f32 [D]                                               */
-    const void* w_qkv; const void* b_qkv;     /* bf16 [3D,D] (q|k|v rows), f32 [3D] (k part zero)      */
+    const void* w_qkv; const void* c1_qkv; const void* b_qkv; /* bf16 [3D,D] (q|k|v rows) with norm1's gamma folded in,
+                                                                 f32 [3D] c1, f32 [3D] c2 (= bias + W beta; k bias zero) */
     const void* w_o;   const void* b_o;       /* bf16 [D,D], f32 [D]   - LayerScale lambda1 folded in  */
-    const void* ln2_g; const void* ln2_b;     /* f32 [D]                                               */
-    const void* w_up;  const void* b_up;      /* bf16 [I,D], f32 [I]                                   */
+    const void* w_up;  const void* c1_up; const void* b_up;   /* bf16 [I,D] with norm2's gamma folded in, f32 [I] c1, c2 */
     const void* w_down; const void* b_down;   /* bf16 [D,I], f32 [D]   - LayerScale lambda2 folded in  */
 } cbas_layer_weights;
 
@@ -87,10 +95,23 @@ typedef struct cbas_encoder cbas_encoder;
 int cbas_b200_encoder_create(const cbas_encoder_cfg* cfg, const cbas_encoder_weights* w, cbas_encoder** out);
 void cbas_b200_encoder_destroy(cbas_encoder* enc);
 
+/* Per-handle test knobs (every setting computes the same function; the parity tests run them against each other). */
+#define CBAS_OPT_ATTENTION_IMPL 0   /* 0 = automatic (tcgen05 whenever a tcgen05 kernel covers the token count),
+                                       1 = mma.sync kernel, 2 = tcgen05 kernel                                    */
+#define CBAS_OPT_PRUNE_LAST_LAYER 1 /* 1 (default) = in the last block compute only what the pooled CLS row needs (K/V
+                                       for all tokens, the rest for the CLS rows), 0 = run it on every token       */
+#define CBAS_OPT_RESIZE_KERNEL 2    /* PROCESSOR mode: 2 (default) = column-per-thread kernel when the geometry allows,
+                                       1 = general shared-memory tiled kernel, 0 = per-pixel kernel                 */
+int cbas_b200_encoder_set_option(cbas_encoder* enc, int32_t option, int32_t value);
+
 /* frames_dev: uint8 RGB HWC (what decord's get_batch(...).asnumpy() yields, cbas.py:425), n frames,
  * frame_stride / row_stride in bytes.  emb_out_dev: f32 [n, D] pooled CLS embedding after the final norm. */
 int cbas_b200_encoder_forward_u8(cbas_encoder* enc, const uint8_t* frames_dev, int32_t n, int64_t frame_stride,
                                  int32_t row_stride, float* emb_out_dev, void* stream);
+/* REFERENCE mode only: the frames as ONE uint8 plane each (the green channel, cbas.py:431 `frames_np[:, :, :, 1]`),
+ * n planes of in_h x in_w bytes, strides in bytes - a third of the host-to-device traffic of the RGB frames. */
+int cbas_b200_encoder_forward_u8_plane(cbas_encoder* enc, const uint8_t* planes_dev, int32_t n, int64_t frame_stride,
+                                       int32_t row_stride, float* emb_out_dev, void* stream);
 /* DinoEncoder.__call__ compatibility (cbas.py:435,672): planes_dev f32 [n, in_h, in_w] in [0,1] (REFERENCE only). */
 int cbas_b200_encoder_forward_f32(cbas_encoder* enc, const float* planes_dev, int32_t n, float* emb_out_dev,
                                   void* stream);
@@ -104,16 +125,30 @@ int cbas_b200_encoder_debug_hidden(cbas_encoder* enc, const uint8_t* frames_dev,
  * 5 bias+GELU->f32 */
 int cbas_b200_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_dev, void* out_dev, int32_t M,
                         int32_t N, int32_t K, int32_t epi, void* stream);
-/* Profiling aid: device buffer of 64*16 int64 that CTA 0 of the tcgen05 attention kernel fills with clock64()
- * stamps per pipeline stage (null switches it off). */
+/* Fused LayerNorm, kernel level (what the encoder chains per block; csrc/gemm_tcgen05.cuh).  Row statistics are
+ * 36 floats per row: [0,16) partial sums of y = h - shift, [16,32) partial sums of y^2, [32] shift, [33,36) padding.
+ *   ln_stats_init: exact statistics of h f32 [rows, D] (shift = row mean) and hb = bf16(h - shift)
+ *   gemm_resid_ln: h += A[M,K] W[N,K]^T + bias in place (N = D <= 1024), hb_out = bf16(h - new shift), stats_out from
+ *                  stats_in (the new shift is the exact row mean before the update); stats_in != stats_out
+ *   gemm_ln_a:     out bf16 [M,N] = epi(LN(h) W^T + b) computed from hb / stats with the folded weight W' = W * gamma,
+ *                  c1[n] = sum_k W'[n,k], c2[n] = sum_k W[n,k] beta[k] + b[n]; K = D; epi 0 (bias) or 1 (bias + GELU) */
+int cbas_b200_ln_stats_init(float* h_dev, void* hb_out_dev, float* stats_out_dev, int32_t rows, int32_t D,
+                            void* stream);
+int cbas_b200_gemm_resid_ln(const void* a_dev, const void* w_dev, const float* bias_dev, float* h_dev, void* hb_out_dev,
+                            const float* stats_in_dev, float* stats_out_dev, int32_t M, int32_t N, int32_t K,
+                            void* stream);
+int cbas_b200_gemm_ln_a(const void* hb_dev, const float* stats_dev, const void* w_folded_dev, const float* c1_dev,
+                        const float* c2_dev, void* out_bf16_dev, int32_t M, int32_t N, int32_t K, int32_t epi,
+                        float eps, void* stream);
+/* Profiling aid (per host thread): device buffer of 64*16 int64 that CTA 0 of the tcgen05 attention kernel fills with
+ * clock64() stamps per pipeline stage (null switches it off). */
 int cbas_b200_debug_attention_trace(void* trace_dev);
-/* Test knob: 1 (default) = in the last block compute only what the pooled CLS row needs (K/V for all tokens, the
- * rest for the CLS rows), 0 = run the last block on every token.  Same result for the row that is kept. */
-int cbas_b200_debug_prune_last_layer(int32_t on);
-/* Test knob: 2 (default) = column-per-thread resize kernel when the geometry allows (<= 256 output columns, <= 5 taps),
- * 1 = general shared-memory tiled kernel, 0 = per-pixel kernel.  All three agree (1 and 2 bitwise). */
+/* Test knob for cbas_b200_preprocess_resize (per host thread): 2 (default) = column-per-thread resize kernel when the
+ * geometry allows (<= 256 output columns, <= 5 taps), 1 = general shared-memory tiled kernel, 0 = per-pixel kernel.
+ * All three agree (1 and 2 bitwise). */
 int cbas_b200_debug_resize_tiled(int32_t on);
-/* Test knob: 0 = choose automatically (CTA pairs / tcgen05 cta_group::2 when M >= 4096), 1 or 2 = force. */
+/* Test knob for the GEMM launcher (per host thread): 0 = choose automatically (CTA pairs / tcgen05 cta_group::2 when
+ * M >= 4096), 1 or 2 = force. */
 int cbas_b200_debug_gemm_cta_group(int32_t cg);
 int cbas_b200_layernorm(const float* in_dev, const float* gamma_dev, const float* beta_dev, void* out_bf16_dev,
                         int32_t rows, int32_t D, float eps, void* stream);
@@ -129,9 +164,6 @@ int cbas_b200_attention_tc_supported(int32_t T, int32_t prefix, int32_t rope);
 int cbas_b200_attention_tc(const void* qkv_bf16_dev, void* out_bf16_dev, const float* rope_cos_dev,
                            const float* rope_sin_dev, int32_t frames, int32_t T, int32_t prefix, int32_t heads,
                            void* stream);
-/* Test knob: 0 = automatic (tcgen05 when T <= 256), 1 = mma.sync kernel, 2 = tcgen05 kernel (both rotate q and k
- * in their prologue). */
-int cbas_b200_debug_attention_impl(int32_t impl);
 int cbas_b200_preprocess_green(const uint8_t* frames_dev, void* a_bf16_dev, int32_t n, int32_t H, int32_t W,
                                int64_t frame_stride, int32_t row_stride, void* stream);
 int cbas_b200_preprocess_resize(const uint8_t* frames_dev, void* a_bf16_dev, int32_t n, int32_t H, int32_t W,

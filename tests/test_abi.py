@@ -26,7 +26,7 @@ def test_header_symbols_exported_and_bound():
 
 def test_abi_version_and_error_channel():
     lib = _lib.lib()
-    assert lib.cbas_b200_abi_version() == 2
+    assert lib.cbas_b200_abi_version() == _lib.ABI_VERSION == 3
     assert isinstance(lib.cbas_b200_launch_count(), int)
     # argument validation happens before any CUDA call, so this is safe without a GPU
     rc = lib.cbas_b200_encoder_create(None, None, None)
@@ -36,7 +36,7 @@ def test_abi_version_and_error_channel():
 def test_struct_layouts_match_header():
     # sizes the C compiler produces for the header's structs (LP64): guards against field drift
     assert ctypes.sizeof(_lib.EncoderCfg) == 14 * 4
-    assert ctypes.sizeof(_lib.LayerWeights) == 12 * 8
+    assert ctypes.sizeof(_lib.LayerWeights) == 10 * 8
     assert ctypes.sizeof(_lib.EncoderWeights) == 13 * 8
     assert ctypes.sizeof(_lib.HeadCfg) == 9 * 4
     assert ctypes.sizeof(_lib.HeadWeights) == 28 * 8 + 8 + 8 * 8  # + the second LSTM layer

@@ -34,11 +34,23 @@ class _FakePipeline:
             sink(e)
         return self.seen
 
+    def run_reader(self, reader, video_len, sink, progress_callback=None):
+        """what StreamedEncoder.run_reader does, minus the GPU: read_into a staging array chunk by chunk"""
+        def chunks():
+            for s in range(0, video_len, cbas.CHUNK_SIZE):
+                e = min(s + cbas.CHUNK_SIZE, video_len)
+                buf = np.empty((e - s,) + tuple(reader.frame_hw) + (3,), np.uint8)
+                reader.read_into(s, e, buf)
+                if progress_callback:
+                    progress_callback(e / video_len * 100)
+                yield buf
+        return self.run(chunks(), sink)
+
 
 def _fake_encoder(width=768):
     enc = DinoEncoder.__new__(DinoEncoder)
     nn.Module.__init__(enc)
-    enc.hidden_size, enc.device = width, torch.device("cpu")
+    enc.hidden_size, enc.device, enc.preprocess = width, torch.device("cpu"), "processor"
     return enc
 
 
@@ -53,7 +65,7 @@ def clip(tmp_path):
 def test_encode_file_contract(monkeypatch, clip):
     path, frames = clip
     pipe = _FakePipeline(768)
-    monkeypatch.setattr(cbas, "_make_pipeline", lambda enc, hw: pipe)
+    monkeypatch.setattr(cbas, "_make_pipeline", lambda enc, hw, planes=False: pipe)
     monkeypatch.setattr(gui_state, "proj", types.SimpleNamespace(encoder_model_identifier="facebook/dinov3-vitb16-pretrain-lvd1689m"))
     progress = []
     out = cbas.encode_file(_fake_encoder(), path, progress.append)
@@ -70,7 +82,7 @@ def test_encode_file_contract(monkeypatch, clip):
 
 def test_encode_file_unstamped_without_project(monkeypatch, clip):
     path, _ = clip
-    monkeypatch.setattr(cbas, "_make_pipeline", lambda enc, hw: _FakePipeline(384))
+    monkeypatch.setattr(cbas, "_make_pipeline", lambda enc, hw, planes=False: _FakePipeline(384))
     monkeypatch.setattr(gui_state, "proj", None)
     out = cbas.encode_file(_fake_encoder(384), path)
     with store.EmbeddingReader(out) as r:
@@ -79,7 +91,7 @@ def test_encode_file_unstamped_without_project(monkeypatch, clip):
 
 def test_encode_file_failure_removes_tmp_and_raises(monkeypatch, clip):
     path, _ = clip
-    monkeypatch.setattr(cbas, "_make_pipeline", lambda enc, hw: _FakePipeline(768, fail_at=512))
+    monkeypatch.setattr(cbas, "_make_pipeline", lambda enc, hw, planes=False: _FakePipeline(768, fail_at=512))
     with pytest.raises(RuntimeError, match="injected"):
         cbas.encode_file(_fake_encoder(), path)
     d = os.path.dirname(path)
@@ -87,7 +99,7 @@ def test_encode_file_failure_removes_tmp_and_raises(monkeypatch, clip):
 
 
 def test_encode_file_empty_and_bad_inputs(monkeypatch, tmp_path):
-    monkeypatch.setattr(cbas, "_make_pipeline", lambda enc, hw: _FakePipeline(768))
+    monkeypatch.setattr(cbas, "_make_pipeline", lambda enc, hw, planes=False: _FakePipeline(768))
     p = str(tmp_path / "empty.npy")
     np.save(p, np.zeros((0, 32, 32, 3), np.uint8))
     assert cbas.encode_file(_fake_encoder(), p) is None            # zero frames -> None (cbas.py:405-407)

