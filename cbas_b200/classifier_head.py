@@ -174,6 +174,38 @@ class ClassifierLSTMDeltas(nn.Module):
         return (probs, logits) if return_logits else probs
 
 
+def synthetic_head_state_dict(in_features: int = 768, out_features: int = 9, bottleneck_dim: int = 128,
+                              lstm_hidden_size: int = 64, lstm_layers: int = 1, use_acceleration: bool = True,
+                              seed: int = 0, scale: float = 2.0):
+    """Random head weights in the reference's `model.pth` layout (workthreads.py:856): nn.Linear / nn.LSTM-style
+    uniform(+-scale / sqrt(fan_in)), LayerNorm gains near 1.  For benchmarks and smoke runs (no trained bundle ships
+    with the repo); load with `ClassifierLSTMDeltas(...).load_state_dict(sd)`."""
+    g = torch.Generator().manual_seed(seed)
+
+    def u(shape, fan_in):
+        b = scale / fan_in ** 0.5
+        return (torch.rand(shape, generator=g) * 2 - 1) * b
+
+    Hs, Bn, Fi, Co = lstm_hidden_size, bottleneck_dim, in_features, out_features
+    sd = {"gate": torch.tensor(0.2), "attention_temp": torch.tensor(1.0)}
+    streams = ("cls", "delta", "acc") if use_acceleration else ("cls", "delta")
+    for s in streams:
+        sd[f"{s}_bottleneck.0.weight"], sd[f"{s}_bottleneck.0.bias"] = u((Bn, Fi), Fi), u((Bn,), Fi)
+        sd[f"{s}_ln.weight"] = 1.0 + 0.1 * torch.randn(Bn, generator=g)
+        sd[f"{s}_ln.bias"] = 0.1 * torch.randn(Bn, generator=g)
+    aug = len(streams) * Bn
+    sd["lin0.0.weight"], sd["lin0.0.bias"] = u((256, aug), aug), u((256,), aug)
+    sd["attention_head.weight"], sd["attention_head.bias"] = u((1, 2 * Hs), 2 * Hs), u((1,), 2 * Hs)
+    sd["lin1.weight"], sd["lin1.bias"] = u((Co, Fi), Fi), u((Co,), Fi)
+    sd["lin2.weight"], sd["lin2.bias"] = u((Co, 2 * Hs), 2 * Hs), u((Co,), 2 * Hs)
+    for layer in range(lstm_layers):
+        kin = 256 if layer == 0 else 2 * Hs
+        for sfx in ("", "_reverse"):
+            sd[f"lstm.weight_ih_l{layer}{sfx}"], sd[f"lstm.weight_hh_l{layer}{sfx}"] = u((4 * Hs, kin), Hs), u((4 * Hs, Hs), Hs)
+            sd[f"lstm.bias_ih_l{layer}{sfx}"], sd[f"lstm.bias_hh_l{layer}{sfx}"] = u((4 * Hs,), Hs), u((4 * Hs,), Hs)
+    return sd
+
+
 def actogram_bins(probs: torch.Tensor, behavior: int, threshold: float, bin_frames: int) -> torch.Tensor:
     """Numeric core of Actogram.__init__ (cbas.py:969-999) on the GPU: probs float32 [N,C] (CUDA) -> int32 bin
     counts [ceil(N / bin_frames)]."""

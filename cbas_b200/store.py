@@ -27,6 +27,11 @@ CHUNK_ROWS = 8192
 SCHEMA_VERSION = "1.0"
 
 
+def backend_name() -> str:
+    """'h5py' when the reference's own HDF5 library is importable, else the native writer/reader."""
+    return "h5py" if HAVE_H5PY else "native"
+
+
 class EmbeddingWriter:
     """Append float16 rows to a new embedding file."""
 

@@ -181,3 +181,27 @@ def test_head_live_against_reference_module():
     got, got_raw = ohead.head_forward(sd, x)
     np.testing.assert_allclose(got.numpy(), want.numpy(), atol=3e-5, rtol=1e-4)
     np.testing.assert_allclose(got_raw.numpy(), want_raw.numpy(), atol=3e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("variant", [dict(), dict(lstm_hidden=128, lstm_layers=2), dict(use_acceleration=False)])
+def test_eager_head_baseline_is_the_same_function(golden_dir, variant):
+    """oracle/eager_gpu.EagerHead (the torch-eager / cuDNN baseline bench.py times on the GPU) against the pinned
+    restatement, and its infer loop against the reference's infer_file fixture."""
+    from oracle import eager_gpu
+    sd = ohead.make_head_state(96, 5, 128, variant.get("lstm_hidden", 64), seed=4, scale=1.5,
+                               lstm_layers=variant.get("lstm_layers", 1),
+                               use_acceleration=variant.get("use_acceleration", True))
+    m = eager_gpu.eager_head_from_state(sd, 96, 5)
+    x = torch.randn(9, 31, 96)
+    with torch.no_grad():
+        got, raw = m(x)
+    want, want_raw = ohead.head_forward(sd, x)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), atol=3e-5, rtol=1e-4)
+    np.testing.assert_allclose(raw.numpy(), want_raw.numpy(), atol=3e-5, rtol=1e-4)
+    if not variant:
+        g = _g(golden_dir, "infer_file.npz")
+        sd = ohead.make_head_state(768, 9, 128, 64, seed=int(g["state_seed"]), scale=float(g["state_scale"]))
+        emb = (np.random.default_rng(int(g["emb_seed"])).standard_normal((130, 768)) * float(g["emb_scale"])).astype(np.float16)
+        probs = eager_gpu.eager_infer_loop(eager_gpu.eager_head_from_state(sd, 768, 9), emb, 31, "cpu",
+                                           temperature=float(g["temperature"]))
+        np.testing.assert_allclose(probs, g["probs"], atol=2e-6)
