@@ -19,6 +19,10 @@
 
 using namespace cbas;
 
+#ifndef CBAS_LN_FUSED_DEFAULT
+#define CBAS_LN_FUSED_DEFAULT 1
+#endif
+
 namespace {
 
 // float planes [n,H,W] in [0,1] (DinoEncoder.__call__ input, cbas.py:435) -> folded-K patch matrix (x*255 as bf16)
@@ -252,6 +256,9 @@ struct cbas_encoder {
     bool prune_last_layer = true;      // false: run the last block on every token
     int attention_impl = 0;            // 0 auto, 1 mma.sync, 2 tcgen05
     int resize_tiled = 2;              // 0 per-pixel kernel, 1 general tiled kernel, 2 column-per-thread kernel
+    int ln_fused = CBAS_LN_FUSED_DEFAULT;  // 1: norm1 / norm2 inside the GEMM epilogues, 0: standalone LayerNorm kernels
+    float* ones = nullptr;             // [D] ones / zeros: unit gamma and zero beta for the standalone LayerNorm path
+    float* zeros = nullptr;            //     (gamma and beta themselves are folded into the weights either way)
     // workspace (device)
     __nv_bfloat16* a_patch = nullptr;  // [max*Np, Kp]
     float* h = nullptr;                // [max*T, D]   residual stream
@@ -364,7 +371,67 @@ GemmParams ln_producer(const cbas_encoder* e, int M, int K, const void* bias, in
     return p;
 }
 
+// The same block with norm1 / norm2 as standalone kernels (CBAS_OPT_LN_FUSION 0).  gamma and beta are folded into the
+// QKV / up weights for both paths (W' = W * gamma, c2 = W beta + b), so this path normalises with unit gamma / zero
+// beta and runs the plain GEMMs on W' and c2: the same function, the LayerNorm arithmetic in its own HBM pass.
+int encoder_layer_unfused(cbas_encoder* e, int li, int n, cudaStream_t s, bool cls_only) {
+    const cbas_encoder_cfg& c = e->cfg;
+    const cbas_layer_weights& L = e->layers[li];
+    const int D = c.hidden, I = c.intermediate, T = e->T, M = n * T;
+    const bool tc = use_attention_tc(e->attention_impl, T, c.prefix_tokens, e->w.rope_cos != nullptr);
+    if (int rc = launch_layernorm<__nv_bfloat16>(e->h, 1, e->ones, e->zeros, e->hb, M, D, c.ln_eps, s)) return rc;
+    const __nv_bfloat16* wqkv = (const __nv_bfloat16*)L.w_qkv;
+    const float* bqkv = (const float*)L.b_qkv;
+    GemmParams p{};
+    if (!cls_only) {
+        p.M = M; p.N = 3 * D; p.K = D; p.bias = bqkv; p.out = e->qkv; p.ldo = 3 * D; p.f16_from = 2 * D;
+        if (int rc = launch_gemm(e->hb, D, wqkv, D, p, tc ? EPI_BIAS_BF16_VF16 : EPI_BIAS_BF16, s, PROF_QKV_GEMM)) return rc;
+        if (tc) {
+            if (int rc = launch_attention_tc(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n, T,
+                                             c.prefix_tokens, c.heads, s)) return rc;
+        } else if (int rc = launch_attention(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n, T,
+                                             c.prefix_tokens, c.heads, s)) return rc;
+        p = GemmParams{};
+        p.M = M; p.N = D; p.K = D; p.bias = (const float*)L.b_o; p.out = e->h; p.ldo = D;
+        if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_o, D, p, EPI_RESID_F32, s, PROF_PROJ_GEMM)) return rc;
+        if (int rc = launch_layernorm<__nv_bfloat16>(e->h, 1, e->ones, e->zeros, e->hb, M, D, c.ln_eps, s)) return rc;
+        p = GemmParams{};
+        p.M = M; p.N = I; p.K = D; p.bias = (const float*)L.b_up; p.out = e->u; p.ldo = I;
+        if (int rc = launch_gemm(e->hb, D, (const __nv_bfloat16*)L.w_up, D, p, EPI_BIAS_GELU_BF16, s, PROF_UP_GEMM)) return rc;
+        p = GemmParams{};
+        p.M = M; p.N = D; p.K = I; p.bias = (const float*)L.b_down; p.out = e->h; p.ldo = D;
+        return launch_gemm(e->u, I, (const __nv_bfloat16*)L.w_down, I, p, EPI_RESID_F32, s, PROF_DOWN_GEMM);
+    }
+    // last block, CLS rows only (see encoder_last_layer_cls_only)
+    p.M = M; p.N = 2 * D; p.K = D; p.bias = bqkv + D; p.out = e->qkv + D; p.ldo = 3 * D; p.f16_from = D;
+    if (int rc = launch_gemm(e->hb, D, wqkv + (size_t)D * D, D, p, tc ? EPI_BIAS_BF16_VF16 : EPI_BIAS_BF16, s,
+                             PROF_QKV_GEMM)) return rc;
+    p = GemmParams{};
+    p.M = n; p.N = D; p.K = D; p.bias = bqkv; p.out = e->cls_q; p.ldo = D;
+    if (int rc = launch_gemm(e->hb, T * D, wqkv, D, p, EPI_BIAS_BF16, s, PROF_QKV_GEMM)) return rc;
+    {
+        ProfScope prof(PROF_ATTENTION, s);
+        const int items = n * c.heads;
+        cls_attention_kernel<<<(items * 32 + 127) / 128, 128, 0, s>>>(
+            e->cls_q, e->qkv, e->cls_att, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n, T,
+            e->w.rope_cos ? c.prefix_tokens : T, c.heads, D, 0.125f * 1.4426950408889634f, tc ? 1 : 0);
+        count_launch();
+        if (int rc = check_cuda(cudaGetLastError(), "cls_attention_kernel launch")) return rc;
+    }
+    p = GemmParams{};
+    p.M = n; p.N = D; p.K = D; p.bias = (const float*)L.b_o; p.out = e->h; p.ldo = T * D;
+    if (int rc = launch_gemm(e->cls_att, D, (const __nv_bfloat16*)L.w_o, D, p, EPI_RESID_F32, s, PROF_PROJ_GEMM)) return rc;
+    if (int rc = launch_layernorm<__nv_bfloat16>(e->h, T, e->ones, e->zeros, e->cls_hb, n, D, c.ln_eps, s)) return rc;
+    p = GemmParams{};
+    p.M = n; p.N = I; p.K = D; p.bias = (const float*)L.b_up; p.out = e->u; p.ldo = I;
+    if (int rc = launch_gemm(e->cls_hb, D, (const __nv_bfloat16*)L.w_up, D, p, EPI_BIAS_GELU_BF16, s, PROF_UP_GEMM)) return rc;
+    p = GemmParams{};
+    p.M = n; p.N = D; p.K = I; p.bias = (const float*)L.b_down; p.out = e->h; p.ldo = T * D;
+    return launch_gemm(e->u, I, (const __nv_bfloat16*)L.w_down, I, p, EPI_RESID_F32, s, PROF_DOWN_GEMM);
+}
+
 int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
+    if (!e->ln_fused) return encoder_layer_unfused(e, li, n, s, false);
     const cbas_encoder_cfg& c = e->cfg;
     const cbas_layer_weights& L = e->layers[li];
     const int D = c.hidden, I = c.intermediate, M = n * e->T;
@@ -398,6 +465,7 @@ int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
 // K and V are projected for every token but the query, attention output, proj, norm2 and the MLP run on the n CLS
 // rows alone.  Mathematically identical to the full block for the row that is kept.
 int encoder_last_layer_cls_only(cbas_encoder* e, int li, int n, cudaStream_t s) {
+    if (!e->ln_fused) return encoder_layer_unfused(e, li, n, s, true);
     const cbas_encoder_cfg& c = e->cfg;
     const cbas_layer_weights& L = e->layers[li];
     const int D = c.hidden, I = c.intermediate, T = e->T, M = n * T;
@@ -507,6 +575,13 @@ int cbas_b200_encoder_create(const cbas_encoder_cfg* cfg, const cbas_encoder_wei
         alloc((void**)&e->stats[i], mt * LN_STAT_FLOATS * 4);
         if (err == cudaSuccess) err = cudaMemset(e->stats[i], 0, mt * LN_STAT_FLOATS * 4);
     }
+    alloc((void**)&e->ones, D * 4);
+    alloc((void**)&e->zeros, D * 4);
+    if (err == cudaSuccess) {
+        std::vector<float> one(D, 1.0f);
+        err = cudaMemcpy(e->ones, one.data(), D * 4, cudaMemcpyHostToDevice);
+        if (err == cudaSuccess) err = cudaMemset(e->zeros, 0, D * 4);
+    }
     alloc((void**)&e->cls_hb, (size_t)cfg->max_frames * D * 2);
     alloc((void**)&e->cls_stats, (size_t)cfg->max_frames * LN_STAT_FLOATS * 4);
     if (err == cudaSuccess) err = cudaMemset(e->cls_stats, 0, (size_t)cfg->max_frames * LN_STAT_FLOATS * 4);
@@ -528,7 +603,7 @@ void cbas_b200_encoder_destroy(cbas_encoder* e) {
     DeviceGuard guard(e->device);
     cudaFree(e->a_patch); cudaFree(e->h); cudaFree(e->xn); cudaFree(e->qkv); cudaFree(e->u);
     cudaFree(e->hb); cudaFree(e->stats[0]); cudaFree(e->stats[1]); cudaFree(e->cls_hb); cudaFree(e->cls_stats);
-    cudaFree(e->cls_q); cudaFree(e->cls_att);
+    cudaFree(e->cls_q); cudaFree(e->cls_att); cudaFree(e->ones); cudaFree(e->zeros);
     delete e;
 }
 
@@ -574,6 +649,7 @@ int cbas_b200_encoder_set_option(cbas_encoder* enc, int32_t option, int32_t valu
             return 0;
         case CBAS_OPT_PRUNE_LAST_LAYER: enc->prune_last_layer = value != 0; return 0;
         case CBAS_OPT_RESIZE_KERNEL: enc->resize_tiled = value < 0 ? 0 : (value > 2 ? 2 : value); return 0;
+        case CBAS_OPT_LN_FUSION: enc->ln_fused = value != 0; return 0;
     }
     return fail("unknown encoder option " + std::to_string(option));
 }

@@ -12,9 +12,10 @@
 //   warp 16  : TMA producer (whole warp walks the loop, one elected lane issues)
 //   warp 17  : MMA issuer   (same; with CTA pairs only the leader CTA's warp issues)
 //   warp 18  : TMEM allocator / deallocator
-//   warp 19  : LayerNorm-consumer GEMMs only: per tile, one tile ahead of the epilogue, turns the 128 rows' partial
-//              sums into {rstd, -mean * rstd} in shared memory and pulls the tile's column constants into L1 (the
-//              epilogue warps are the busiest part of these kernels and must not wait for global loads); else idle
+//   warp 19  : fused-LayerNorm GEMMs only: per tile, one tile ahead of the epilogue, turns the 128 rows' partial sums
+//              into {rstd, -mean * rstd} (consumer) or the new row shift (producer) in shared memory and pulls the
+//              tile's column constants into L1 (the epilogue warps are the busiest part of these kernels and must not
+//              wait for global loads); else idle
 //   warps 0-15: epilogue, two groups of eight warps.  Warp w may only read TMEM lanes 32*(w%4)..+31, so a group
 //              has two warps per lane quarter and each takes half of the slab's columns (64 B of every row).
 //              A group owns one 16 KB staging slab (128 rows x 128 B) and walks the tile's column slabs
@@ -276,36 +277,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     } else if (warp == GEMM_EPI_WARPS + 3) {
-        // ---------------------------------------------------------------- LayerNorm-consumer helper
-        if constexpr (kOutBf16) {
+        // ---------------------------------------------------------------- LayerNorm helper (consumer and producer)
+        if constexpr (kOutBf16 || kLnProducer) {
             if (p.ln_in) {
                 int iter = 0;
                 for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++iter) {
                     const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
                     const int m_base = (m_blk * CG + (int)cta_rank) * GEMM_BLOCK_M;
-                    // this tile's c2 / c1 (BLOCK_N floats each): first touch by this warp, L1 hits for the epilogue
+                    // this tile's per-column constants (BLOCK_N floats each): first touch by this warp, L1 hits for the
+                    // epilogue warps
                     if (lane * 32 < BLOCK_N) {
-                        prefetch_l1(p.bias + n_blk * BLOCK_N + lane * 32);
-                        prefetch_l1(p.ln_c1 + n_blk * BLOCK_N + lane * 32);
+                        if (p.bias) prefetch_l1(p.bias + n_blk * BLOCK_N + lane * 32);
+                        if (!kLnProducer) prefetch_l1(p.ln_c1 + n_blk * BLOCK_N + lane * 32);
                     }
                     float2 rc[GEMM_BLOCK_M / 32];
 #pragma unroll
                     for (int r = 0; r < GEMM_BLOCK_M / 32; ++r) {
                         const int row = m_base + r * 32 + lane;
-                        float t = 0.f, q = 0.f;
+                        float t = 0.f, q = 0.f, s_old = 0.f;
                         if (row < p.M) {
                             const float4* st = reinterpret_cast<const float4*>(
                                 p.ln_in + (size_t)row * p.ln_in_stride * LN_STAT_FLOATS);
 #pragma unroll
                             for (int i = 0; i < LN_STAT_SLOTS / 4; ++i) {
-                                const float4 a = __ldg(st + i), c = __ldg(st + LN_STAT_SLOTS / 4 + i);
+                                const float4 a = ld_cg_f4(st + i);
                                 t += (a.x + a.y) + (a.z + a.w);
-                                q += (c.x + c.y) + (c.z + c.w);
+                                if (!kLnProducer) {
+                                    const float4 c = ld_cg_f4(st + LN_STAT_SLOTS / 4 + i);
+                                    q += (c.x + c.y) + (c.z + c.w);
+                                }
                             }
+                            if (kLnProducer) s_old = ld_cg_f1(reinterpret_cast<const float*>(st) + 2 * LN_STAT_SLOTS);
                         }
                         const float mu = t * p.ln_inv_dim, ms = q * p.ln_inv_dim;
-                        const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ms), 0.f) + p.ln_eps);
-                        rc[r] = make_float2(rstd, -mu * rstd);
+                        if (kLnProducer) {
+                            // the row's new shift: its exact mean before this update (old shift + mean of the old y)
+                            rc[r] = make_float2(s_old + mu, 0.f);
+                        } else {
+                            const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ms), 0.f) + p.ln_eps);
+                            rc[r] = make_float2(rstd, -mu * rstd);
+                        }
                     }
                     mbar_wait(rowc_empty, (iter & 1) ^ 1);  // the epilogue has taken the previous tile's values
 #pragma unroll
@@ -348,19 +359,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
                 const int row = m_base + row_in_tile;
                 const bool row_ok = row < p.M;
-                // new shift = exact mean of the row before this update (old shift + mean of the old y)
-                float shift = 0.f;
-                if (row_ok) {
-                    const float4* st =
-                        reinterpret_cast<const float4*>(p.ln_in + (size_t)row * p.ln_in_stride * LN_STAT_FLOATS);
-                    float t = 0.f;
-#pragma unroll
-                    for (int i = 0; i < LN_STAT_SLOTS / 4; ++i) {
-                        const float4 a = __ldg(st + i);
-                        t += (a.x + a.y) + (a.z + a.w);
-                    }
-                    shift = fmaf(t, p.ln_inv_dim, __ldg(reinterpret_cast<const float*>(st) + 2 * LN_STAT_SLOTS));
-                }
+                // new shift = exact mean of the row before this update, prepared one tile ahead by the helper warp
+                mbar_wait(rowc_full, iter & 1);
+                const float shift = rowc[row_in_tile].x;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(rowc_empty);
                 __nv_bfloat16* hb_row = reinterpret_cast<__nv_bfloat16*>(p.hb) + (size_t)(row_ok ? row : 0) * p.ldhb;
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();

@@ -340,6 +340,18 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
     return __bfloat1622float2(v);
 }
 
+// 16-byte load that is cached in L2 only: streaming data (row statistics read once per tile) must not evict the few
+// KB of per-column constants the epilogue warps keep hitting in the small L1 that is left beside 227 KB of shared memory
+__device__ __forceinline__ float4 ld_cg_f4(const void* ptr) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
+    return v;
+}
+__device__ __forceinline__ float ld_cg_f1(const void* ptr) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(ptr));
+    return v;
+}
 __device__ __forceinline__ void prefetch_l1(const void* ptr) {
     asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
 }

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
@@ -391,6 +392,9 @@ class DinoEncoder(nn.Module):
             if mode == PRE_REFERENCE and in_hw[0] != in_hw[1]:
                 raise ValueError("reference preprocessing expects square frames (cbas.py:768-784 records square clips)")
             nat = _NativeEncoder(self.config, self._sd, self.device, mode, in_hw, side, self.max_frames)
+            env = os.environ.get("CBAS_B200_LN_FUSION")  # A/B timing: 0 = standalone LayerNorm kernels, 1 = fused
+            if env is not None and _lib.OPT_LN_FUSION not in self._options:
+                nat.set_option(_lib.OPT_LN_FUSION, int(env))
             for opt, val in self._options.items():
                 nat.set_option(opt, val)
             self._native[key] = nat

@@ -102,6 +102,8 @@ void cbas_b200_encoder_destroy(cbas_encoder* enc);
                                        for all tokens, the rest for the CLS rows), 0 = run it on every token       */
 #define CBAS_OPT_RESIZE_KERNEL 2    /* PROCESSOR mode: 2 (default) = column-per-thread kernel when the geometry allows,
                                        1 = general shared-memory tiled kernel, 0 = per-pixel kernel                 */
+#define CBAS_OPT_LN_FUSION 3        /* 1 = norm1 / norm2 fused into the GEMMs around them (csrc/gemm_tcgen05.cuh),
+                                       0 = standalone LayerNorm kernels between the GEMMs (one HBM pass each)       */
 int cbas_b200_encoder_set_option(cbas_encoder* enc, int32_t option, int32_t value);
 
 /* frames_dev: uint8 RGB HWC (what decord's get_batch(...).asnumpy() yields, cbas.py:425), n frames,

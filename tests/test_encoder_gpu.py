@@ -161,6 +161,24 @@ def test_rows_whose_mean_dwarfs_their_spread():
     assert cos >= 0.999 and rel <= 2e-2 and nn_ok
 
 
+@pytest.mark.parametrize("arch,side,n", [("vitb16", 224, 6), ("vits16", 256, 24), ("vitl16", 96, 3)])
+def test_fused_layernorm_matches_standalone_layernorm(arch, side, n):
+    """norm1 / norm2 inside the GEMM epilogues against the same encoder with standalone LayerNorm kernels between the
+    GEMMs (the round-1 arrangement): same weights, same function, different rounding points."""
+    from cbas_b200 import _lib
+    enc = DinoEncoder(f"synthetic:{arch}@4", "cuda", max_frames=24)
+    frames = torch.from_numpy(oenc.synthetic_frames(n, side, side, seed=13)).cuda()
+    enc.set_option(_lib.OPT_LN_FUSION, 1)
+    fused = enc.encode_u8(frames)
+    taps_f = enc.debug_hidden(frames, 2)
+    enc.set_option(_lib.OPT_LN_FUSION, 0)
+    plain = enc.encode_u8(frames)
+    taps_p = enc.debug_hidden(frames, 2)
+    print(f"[parity] fused vs standalone LayerNorm {arch}@{side}: embeddings {rel_err(fused, plain):.3e}, "
+          f"residual stream after 2 blocks {rel_err(taps_f, taps_p):.3e}")
+    assert rel_err(taps_f, taps_p) < 6e-3 and rel_err(fused, plain) < 8e-3
+
+
 @pytest.mark.parametrize("arch,side", [("vitb16", 224), ("vits16", 256), ("vitl16", 64)])
 def test_last_layer_cls_only_matches_full_block(arch, side):
     """The production path skips, in the last block, every row the CLS pooling throws away; the kept row must
