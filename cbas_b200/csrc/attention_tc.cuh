@@ -94,11 +94,128 @@ __device__ __forceinline__ void atc_rope_unit(uint8_t* tile, int row, int c, con
     *phi = hi;
 }
 
+
+// packed fp32 pairs (FFMA2 / FADD2: one issue slot for two lanes of arithmetic)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tmov.b64 rc, {%6,%7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+// 2^x for a pair, x <= 0, on the FMA pipe (ex2_poly3 of ptx.cuh with packed arithmetic)
+__device__ __forceinline__ float2 ex2_poly3_pair(float2 x) {
+    x.x = fmaxf(x.x, -30.f);
+    x.y = fmaxf(x.y, -30.f);
+    const float2 t = fadd2(x, make_float2(12582912.f, 12582912.f));
+    const float2 r = fadd2(t, make_float2(-12582912.f, -12582912.f));
+    const float2 f = fadd2(x, make_float2(-r.x, -r.y));
+    float2 p = ffma2(f, make_float2(0.05517089366912842f, 0.05517089366912842f),
+                     make_float2(0.24261131882667542f, 0.24261131882667542f));
+    p = ffma2(p, f, make_float2(0.6932610273361206f, 0.6932610273361206f));
+    p = ffma2(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+    return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23)),
+                       __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
+}
+
+// Softmax of one thread's share [CB, CE) of its query row (a multiple of 16 columns; the row's other share belongs to
+// the partner thread of the same TMEM lane): exact row max (pass 1, exchanged with the partner through shared memory),
+// then p = exp2(s*c - max*c) as f16 pairs written over columns of S this thread has already consumed (pass 2: pair j
+// of 16-column chunk k goes to column CB + 8 k + j).  Both passes keep the TMEM load of the next chunk in flight
+// while the current one is worked on.  Returns the partial row sum.
+template <int TK, int CB, int CE>
+__device__ __forceinline__ float atc_softmax_range(uint32_t t_row, int T, float c, float* my_max, const float* peer_max,
+                                                   int bar_id) {
+    constexpr int W = CE - CB;
+    constexpr bool kEdge = CE == TK;  // the last 16 columns of this share may lie past the frame
+    float mx = -INFINITY;
+    uint32_t cur[16];
+    if constexpr (W > 0) {
+        // pass 1: 16 columns per TMEM load, the next load in flight while the current chunk is reduced
+        constexpr int NC1 = W / 16;
+        uint32_t buf[2][16];
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        tmem_ld_32x16(t_row + CB, buf[0]);
+#pragma unroll
+        for (int k = 0; k < NC1; ++k) {
+            tmem_ld_wait();
+            if (k + 1 < NC1) tmem_ld_32x16(t_row + CB + 16 * (k + 1), buf[(k + 1) & 1]);
+            uint32_t* v = buf[k & 1];
+            if (kEdge && k == NC1 - 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (CB + 16 * k + j >= T) v[j] = 0xff800000u;  // -inf
+            }
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3])));
+            m2 = fmaxf(m2, fmaxf(__uint_as_float(v[4]), __uint_as_float(v[5])));
+            m3 = fmaxf(m3, fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])));
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[8]), __uint_as_float(v[9])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[10]), __uint_as_float(v[11])));
+            m2 = fmaxf(m2, fmaxf(__uint_as_float(v[12]), __uint_as_float(v[13])));
+            m3 = fmaxf(m3, fmaxf(__uint_as_float(v[14]), __uint_as_float(v[15])));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        tmem_ld_32x16(t_row + CB, cur);  // pass 2's first chunk flies during the exchange
+    }
+    *my_max = mx;
+    named_bar_sync(bar_id, 64);  // only the partner warp: same rows, other share of the keys
+    mx = fmaxf(mx, *peer_max);
+    float sum = 0.f;
+    if constexpr (W > 0) {
+        constexpr int NC = W / 16;
+        const float mc = mx * c;
+        const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
+        float2 s0 = make_float2(0.f, 0.f), s1 = s0;
+        uint32_t nxt[16];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            tmem_ld_wait();
+            uint32_t* v = (k & 1) ? nxt : cur;
+            if (k + 1 < NC) tmem_ld_32x16(t_row + CB + 16 * (k + 1), (k & 1) ? cur : nxt);
+            const bool edge = kEdge && k == NC - 1;
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+                if (edge) {
+                    if (CB + 16 * k + 2 * j >= T) a = -INFINITY;
+                    if (CB + 16 * k + 2 * j + 1 >= T) b = -INFINITY;
+                }
+                const float2 x = ffma2(make_float2(a, b), c2, nmc2);
+                float2 e;
+                // the MUFU (16 ex2/clk/SM) is the busiest unit of this kernel: ATC_POLY_PAIRS pairs of every 8 go
+                // through the FMA-pipe polynomial; masked keys stay on the MUFU, where ex2(-inf) is an exact zero
+                if (j < 8 - ATC_POLY_PAIRS || edge) e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                else e = ex2_poly3_pair(x);
+                if (j & 1) s1 = fadd2(s1, e); else s0 = fadd2(s0, e);
+                pk[j] = pack_f16(e.x, e.y);
+            }
+            tmem_st_32x8(t_row + CB + 8 * k, pk);
+        }
+        const float2 st = fadd2(s0, s1);
+        sum = st.x + st.y;
+        tmem_st_wait();
+    }
+    return sum;
+}
+
 #define ATC_STAMP(slot)                                                                       \
     do {                                                                                      \
         if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * ATC_TRACE_SLOTS + (slot)] = clock64();     \
     } while (0)
 
+template <int TK>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 128} over qkv [M, 3D]
                     const __grid_constant__ CUtensorMap tmap_kv,  // box {64, TK}
@@ -107,8 +224,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                     const AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int TK = p.TK, T = p.T;
-    const int set_bytes = atc_set_bytes(TK);
+    static_assert(TK % 16 == 0 && TK >= 16 && TK <= 256, "padded key count");
+    const int T = p.T;
+    constexpr int set_bytes = 2 * 128 * 128 + 2 * TK * 128;
     const bool rope = p.rope_cos != nullptr;
     uint8_t* ostage = smem + 2 * set_bytes;  // [T][128 B] output rows of the current item, swizzled per 128-row tile
     __half2* rope_tab = reinterpret_cast<__half2*>(ostage + atc_stage_bytes(T));  // [T - prefix][32] (cos, sin)
@@ -191,11 +309,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
         // issues.  tcgen05.commit tracks the MMAs of the issuing thread, so the same lane must issue both: elect.sync
         // picks the same lane every time for a full mask.
         const int mt = warp - ATC_MMA_WARP0;
-        const uint32_t idesc_s = umma_idesc_bf16(128, TK);
-        const uint32_t idesc_o = umma_idesc_f16_bmn(128, 64);
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, TK);
+        constexpr uint32_t idesc_o = umma_idesc_f16_bmn(128, 64);
         const uint32_t t_tile = __shfl_sync(0xffffffffu, tmem_base, 0) + 256 * mt;
-        const int nk = TK >> 4;
-        const int ka = (nk + 1) / 2;  // k-steps whose keys belong to the first half of the row
+        constexpr int nk = TK >> 4;
+        constexpr int ka = (nk + 1) / 2;  // k-steps whose keys belong to the first half of the row
         const uint32_t smem_base = smem_u32(smem);
         // start tile 1 half an item late: its MMAs / epilogue then fall into tile 0's softmax and vice versa
         if (mt == 1) mbar_wait(&p_full[0], 0);
@@ -228,11 +346,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                 // keys [CA,TK) at [CA, CA+(TK-CA)/2): each softmax thread overwrites only columns of S that it has
                 // itself already consumed
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (k < nk) {
-                        const uint32_t pcol = 8 * k + (k >= ka ? 8 * ka : 0);
-                        umma_bf16_ts(t_tile + ATC_O_COL, t_tile + pcol, dv + 128 * k, idesc_o, k != 0);
-                    }
+                for (int k = 0; k < nk; ++k) {
+                    const uint32_t pcol = 8 * k + (k >= ka ? 8 * ka : 0);
+                    umma_bf16_ts(t_tile + ATC_O_COL, t_tile + pcol, dv + 128 * k, idesc_o, k != 0);
                 }
                 umma_commit(&o_full[mt]);
                 umma_commit(&v_empty[b]);
@@ -274,8 +390,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
         const bool warp_has_rows = (mt * 128 + quarter * 32) < T;
         const uint32_t t_row = tmem_base + 256 * mt + (uint32_t(quarter * 32) << 16);
         const float c = p.scale_log2;
-        const int CA = ((TK >> 4) + 1) / 2 * 16;  // keys [0,CA) for half 0, [CA,TK) for half 1 (multiples of 16)
-        const int c_begin = half ? CA : 0, c_end = half ? TK : CA;
+        constexpr int CA = ((TK >> 4) + 1) / 2 * 16;  // keys [0,CA) for half 0, [CA,TK) for half 1 (multiples of 16)
         float* my_max = xchg + ((0 * 2 + mt) * 2 + half) * 128 + rit;
         float* peer_max = xchg + ((0 * 2 + mt) * 2 + (half ^ 1)) * 128 + rit;
         float* my_sum = xchg + ((1 * 2 + mt) * 2 + half) * 128 + rit;
@@ -289,75 +404,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             tc_fence_after();
             if (stamper) ATC_STAMP(sbase);
             float sum = 0.f;
-            // pass 1: partial row max over this thread's valid keys
-            float mx = -INFINITY;
-            if (warp_has_rows) {
-                int c0 = c_begin;
-                for (; c0 + 32 <= c_end; c0 += 32) {  // 32 columns per TMEM round trip
-                    uint32_t v[32];
-                    tmem_ld_32x32(t_row + c0, v);
-                    tmem_ld_wait();
-                    if (c0 + 32 <= T) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2)
-                            mx = fmaxf(mx, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
-                    }
-                }
-                if (c0 < c_end) {  // 16-column tail (c_end - c_begin is a multiple of 16)
-                    uint32_t v[16];
-                    tmem_ld_32x16(t_row + c0, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
-                }
-            }
-            *my_max = mx;
-            named_bar_sync(1 + mt * 4 + quarter, 64);  // only the partner warp: same rows, other half of the keys
-            if (stamper) ATC_STAMP(sbase + 1);
-            if (warp_has_rows) {
-                mx = fmaxf(mx, *peer_max);
-                const float mc = mx * c;
-                // pass 2: p = exp2(s*c - max*c) (fp32 MUFU, two results packed into one f16 pair: one instruction fewer
-                // per pair than ex2.approx.f16x2, which the hardware splits into two MUFU ops plus a repack), partial
-                // row sum, written over the consumed part of S
-                for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld_32x16(t_row + c0, v);
-                    tmem_ld_wait();
-                    uint32_t pk[8];
-                    if (c0 + 16 <= T) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            const float x0 = fmaf(__uint_as_float(v[j]), c, -mc);
-                            const float x1 = fmaf(__uint_as_float(v[j + 1]), c, -mc);
-                            // the MUFU (16 ex2/clk/SM) is the busiest unit of this kernel: the last ATC_POLY_PAIRS
-                            // pairs of every 16 go through the FMA-pipe polynomial instead
-                            if ((j >> 1) < 8 - ATC_POLY_PAIRS) pk[j >> 1] = pack_f16(ex2_approx(x0), ex2_approx(x1));  // fp32 MUFU, one pack
-                            else pk[j >> 1] = pack_f16(ex2_poly3(x0), ex2_poly3(x1));
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            const float x0 = (c0 + j < T) ? fmaf(__uint_as_float(v[j]), c, -mc) : -INFINITY;
-                            const float x1 = (c0 + j + 1 < T) ? fmaf(__uint_as_float(v[j + 1]), c, -mc) : -INFINITY;
-                            pk[j >> 1] = ex2_approx_f16x2(pack_f16(x0, x1));
-                        }
-                    }
-                    // chunk sum: f16 pair tree (8 values <= 1 each), then fp32
-                    __half2 a0 = __hadd2(*reinterpret_cast<__half2*>(&pk[0]), *reinterpret_cast<__half2*>(&pk[1]));
-                    __half2 a1 = __hadd2(*reinterpret_cast<__half2*>(&pk[2]), *reinterpret_cast<__half2*>(&pk[3]));
-                    __half2 a2 = __hadd2(*reinterpret_cast<__half2*>(&pk[4]), *reinterpret_cast<__half2*>(&pk[5]));
-                    __half2 a3 = __hadd2(*reinterpret_cast<__half2*>(&pk[6]), *reinterpret_cast<__half2*>(&pk[7]));
-                    const float2 sf = __half22float2(__hadd2(__hadd2(a0, a1), __hadd2(a2, a3)));
-                    sum += sf.x + sf.y;
-                    tmem_st_32x8(t_row + c_begin + ((c0 - c_begin) >> 1), pk);
-                }
-                tmem_st_wait();
+            if (warp_has_rows) {  // the partner warp (same rows) takes the same branch
+                const int bar_id = 1 + mt * 4 + quarter;
+                if (half == 0) sum = atc_softmax_range<TK, 0, CA>(t_row, T, c, my_max, peer_max, bar_id);
+                else sum = atc_softmax_range<TK, CA, TK>(t_row, T, c, my_max, peer_max, bar_id);
             }
             *my_sum = sum;  // read by the partner thread after o_full (ordered through the mbarrier chain)
             tc_fence_before();

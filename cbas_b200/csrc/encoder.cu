@@ -133,6 +133,16 @@ bool use_attention_tc(int impl, int T, int prefix, bool rope = true) {
     return impl >= 2 || attention_tc_fits(T, prefix);
 }
 
+template <int TK>
+int launch_attention_tc_tk(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& to, const CUtensorMap& to1,
+                           const AttnTcParams& p, int smem, int grid, cudaStream_t s) {
+    static DeviceSmemOptIn optin;
+    CBAS_CHECK(optin.ensure(attention_tc_kernel<TK>, smem));
+    attention_tc_kernel<TK><<<grid, ATC_THREADS, smem, s>>>(tq, tkv, to, to1, p);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "attention_tc_kernel launch");
+}
+
 // cs/sn: RoPE tables applied in the kernel's prologue, or null when q and k arrive rotated (EPI_QKV_ROPE_BF16)
 int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* cs, const float* sn, int frames,
                         int T, int prefix, int heads, cudaStream_t s) {
@@ -180,15 +190,17 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const floa
     if (rope && (prefix < 0 || prefix >= T)) return fail("attention: bad prefix token count");
     const int smem = atc_smem_bytes(TK, T, prefix, rope);
     if (smem > 232448) return fail("attention: frame does not fit in shared memory");
-    static DeviceSmemOptIn optin;
-    CBAS_CHECK(optin.ensure(attention_tc_kernel, smem));
     AttnTcParams p{qkv, out, frames, heads, T, TK, D, 0.125f * 1.4426950408889634f, rope ? cs : nullptr,
                    rope ? sn : nullptr, prefix, g_attention_trace};
     const int items = frames * heads;
     const int grid = items < sm_count() ? items : sm_count();
-    attention_tc_kernel<<<grid, ATC_THREADS, smem, s>>>(tq, tkv, to, to1, p);
-    count_launch();
-    return check_cuda(cudaGetLastError(), "attention_tc_kernel launch");
+    switch (TK) {  // the padded key count is a template parameter: every softmax / MMA loop is fully unrolled
+#define ATC_CASE(N) case N: return launch_attention_tc_tk<N>(tq, tkv, to, to1, p, smem, grid, s);
+        ATC_CASE(16) ATC_CASE(32) ATC_CASE(48) ATC_CASE(64) ATC_CASE(80) ATC_CASE(96) ATC_CASE(112) ATC_CASE(128)
+        ATC_CASE(144) ATC_CASE(160) ATC_CASE(176) ATC_CASE(192) ATC_CASE(208) ATC_CASE(224) ATC_CASE(240) ATC_CASE(256)
+#undef ATC_CASE
+    }
+    return fail("attention: unexpected padded key count");
 }
 
 int launch_preprocess_green(const uint8_t* frames, __nv_bfloat16* A, int n, int H, int W, long long fs, int rs,
