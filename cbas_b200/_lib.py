@@ -91,6 +91,7 @@ SIGNATURES = {
                                           c_int32, c_int32, c_int32, c_void_p]),
     "cbas_b200_gemm_ln_a": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                       c_int32, c_int32, c_float, c_void_p]),
+    "cbas_b200_attention_tc_qk_f16": (C.c_int, [c_int32]),
     "cbas_b200_debug_attention_trace": (C.c_int, [c_void_p]),
     "cbas_b200_debug_resize_tiled": (C.c_int, [c_int32]),
     "cbas_b200_debug_gemm_cta_group": (C.c_int, [c_int32]),

@@ -95,6 +95,50 @@ __device__ __forceinline__ void atc_rope_unit(uint8_t* tile, int row, int c, con
 }
 
 
+// The same rotation for an f16 [rows,64] tile (the T <= 256 kernel, whose q and k arrive as f16): packed HFMA2 on f16
+// pairs, cos / sin as f16 from a shared table laid out [pos][chunk pair][8 cos | 8 sin].  `n` (row, chunk pair) units
+// starting at u0 with stride `step` are in flight together so their shared-memory round trips overlap.
+template <int N>
+__device__ __forceinline__ void atc_rope_units_f16(uint8_t* q_tile, uint8_t* k_tile, int u0, int step, int units, int nrot,
+                                                   int prefix, const __half* tab) {
+    uint4 lo[N], hi[N], cs[N], sn[N];
+    uint4* plo[N];
+    uint4* phi[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const int u = u0 + i * step;
+        const int ridx = u < units ? u >> 2 : 0, c4 = u & 3;
+        const int isk = ridx >= nrot;
+        const int tok = prefix + ridx - (isk ? nrot : 0);
+        uint8_t* r = (isk ? k_tile : q_tile) + tok * 128;
+        const int sw = tok & 7;
+        plo[i] = reinterpret_cast<uint4*>(r + ((c4 ^ sw) << 4));
+        phi[i] = reinterpret_cast<uint4*>(r + (((c4 + 4) ^ sw) << 4));
+        const __half* tp = tab + (tok - prefix) * 64 + c4 * 16;
+        lo[i] = *plo[i];
+        hi[i] = *phi[i];
+        cs[i] = *reinterpret_cast<const uint4*>(tp);
+        sn[i] = *reinterpret_cast<const uint4*>(tp + 8);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        __half2* l = reinterpret_cast<__half2*>(&lo[i]);
+        __half2* h = reinterpret_cast<__half2*>(&hi[i]);
+        const __half2* cc = reinterpret_cast<const __half2*>(&cs[i]);
+        const __half2* ss = reinterpret_cast<const __half2*>(&sn[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __half2 a = l[j], b = h[j];
+            l[j] = __hfma2(a, cc[j], __hneg2(__hmul2(b, ss[j])));  // a cos - b sin
+            h[j] = __hfma2(b, cc[j], __hmul2(a, ss[j]));           // b cos + a sin
+        }
+        if (u0 + i * step < units) {
+            *plo[i] = lo[i];
+            *phi[i] = hi[i];
+        }
+    }
+}
+
 // packed fp32 pairs (FFMA2 / FADD2: one issue slot for two lanes of arithmetic)
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     float2 d;
@@ -133,9 +177,10 @@ __device__ __forceinline__ float2 ex2_poly3_pair(float2 x) {
 // then p = exp2(s*c - max*c) as f16 pairs written over columns of S this thread has already consumed (pass 2: pair j
 // of 16-column chunk k goes to column CB + 8 k + j).  Both passes keep the TMEM load of the next chunk in flight
 // while the current one is worked on.  Returns the partial row sum.
-template <int TK, int CB, int CE>
-__device__ __forceinline__ float atc_softmax_range(uint32_t t_row, int T, float c, float* my_max, const float* peer_max,
-                                                   int bar_id) {
+// NP threads share a row; thread `part` publishes its partial max at xmax0 + 512 * part (shared-space address of a
+// [NP][128] float array, already offset to this row) and the NP warps of the lane quarter meet at named barrier bar_id.
+template <int TK, int CB, int CE, int NP>
+__device__ __forceinline__ float atc_softmax_range(uint32_t t_row, int T, float c, uint32_t xmax0, int part, int bar_id) {
     constexpr int W = CE - CB;
     constexpr bool kEdge = CE == TK;  // the last 16 columns of this share may lie past the frame
     float mx = -INFINITY;
@@ -168,9 +213,10 @@ __device__ __forceinline__ float atc_softmax_range(uint32_t t_row, int T, float 
         mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         tmem_ld_32x16(t_row + CB, cur);  // pass 2's first chunk flies during the exchange
     }
-    *my_max = mx;
-    named_bar_sync(bar_id, 64);  // only the partner warp: same rows, other share of the keys
-    mx = fmaxf(mx, *peer_max);
+    st_shared_f32(xmax0 + 512 * part, mx);
+    named_bar_sync(bar_id, 32 * NP);  // only the partner warps: same rows, the other shares of the keys
+#pragma unroll
+    for (int q = 0; q < NP; ++q) mx = fmaxf(mx, ld_shared_f32(xmax0 + 512 * q));
     float sum = 0.f;
     if constexpr (W > 0) {
         constexpr int NC = W / 16;
@@ -210,6 +256,67 @@ __device__ __forceinline__ float atc_softmax_range(uint32_t t_row, int T, float 
     return sum;
 }
 
+
+// The same for shares of at most 64 columns (four threads per row): the whole share is read from TMEM ONCE and stays
+// in registers between the max and the exponentials - no second TMEM pass, no load latency inside the exponential
+// loop, and every pair is independent work for the scheduler.
+template <int TK, int CB, int CE, int NP>
+__device__ __forceinline__ float atc_softmax_range_resident(uint32_t t_row, int T, float c, uint32_t xmax0, int part,
+                                                            int bar_id) {
+    constexpr int W = CE - CB;
+    static_assert(W <= 64 && W % 16 == 0, "register-resident share");
+    constexpr bool kEdge = CE == TK;  // the last 16 columns of this share may lie past the frame
+    float mx = -INFINITY;
+    uint32_t v[W > 0 ? W : 16];
+    if constexpr (W > 0) {
+#pragma unroll
+        for (int k = 0; k < W / 16; ++k) tmem_ld_32x16(t_row + CB + 16 * k, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * k]));
+        tmem_ld_wait();
+        if (kEdge) {
+#pragma unroll
+            for (int j = W - 16; j < W; ++j)
+                if (CB + j >= T) v[j] = 0xff800000u;  // -inf: exp2 gives 0 on the MUFU, 2^-30 -> f16 zero on the FMA pipe
+        }
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < W; j += 8) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+            m2 = fmaxf(m2, fmaxf(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])));
+            m3 = fmaxf(m3, fmaxf(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    }
+    st_shared_f32(xmax0 + 512 * part, mx);
+    named_bar_sync(bar_id, 32 * NP);  // only the partner warps: same rows, the other shares of the keys
+#pragma unroll
+    for (int q = 0; q < NP; ++q) mx = fmaxf(mx, ld_shared_f32(xmax0 + 512 * q));
+    float sum = 0.f;
+    if constexpr (W > 0) {
+        const float mc = mx * c;
+        const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
+        float2 s0 = make_float2(0.f, 0.f), s1 = s0;
+#pragma unroll
+        for (int k = 0; k < W / 16; ++k) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float2 x = ffma2(make_float2(__uint_as_float(v[16 * k + 2 * j]), __uint_as_float(v[16 * k + 2 * j + 1])), c2, nmc2);
+                float2 e;
+                if (j < 8 - ATC_POLY_PAIRS) e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                else e = ex2_poly3_pair(x);
+                if (j & 1) s1 = fadd2(s1, e); else s0 = fadd2(s0, e);
+                pk[j] = pack_f16(e.x, e.y);
+            }
+            tmem_st_32x8(t_row + CB + 8 * k, pk);
+        }
+        const float2 st = fadd2(s0, s1);
+        sum = st.x + st.y;
+        tmem_st_wait();
+    }
+    return sum;
+}
+
 #define ATC_STAMP(slot)                                                                       \
     do {                                                                                      \
         if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * ATC_TRACE_SLOTS + (slot)] = clock64();     \
@@ -229,7 +336,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
     constexpr int set_bytes = 2 * 128 * 128 + 2 * TK * 128;
     const bool rope = p.rope_cos != nullptr;
     uint8_t* ostage = smem + 2 * set_bytes;  // [T][128 B] output rows of the current item, swizzled per 128-row tile
-    __half2* rope_tab = reinterpret_cast<__half2*>(ostage + atc_stage_bytes(T));  // [T - prefix][32] (cos, sin)
+    __half* rope_tab = reinterpret_cast<__half*>(ostage + atc_stage_bytes(T));  // [T - prefix][4 chunk pairs][8 cos | 8 sin]
     float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(rope_tab) + (rope ? atc_rope_bytes(T, p.prefix) : 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + ATC_XCHG_BYTES);
     uint64_t* qk_full = bars;        // [2] TMA -> rotation warps (or MMA when there is no RoPE): Q tiles + K landed
@@ -268,8 +375,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
     }
     if (rope) {
         const int n = (T - p.prefix) * 32;
-        for (int i = threadIdx.x; i < n; i += blockDim.x)
-            rope_tab[i] = __floats2half2_rn(__ldg(p.rope_cos + i), __ldg(p.rope_sin + i));
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int pos = i >> 5, d = i & 31;
+            __half* t = rope_tab + pos * 64 + (d >> 3) * 16 + (d & 7);
+            t[0] = __float2half_rn(__ldg(p.rope_cos + i));
+            t[8] = __float2half_rn(__ldg(p.rope_sin + i));
+        }
     }
     if (warp == ATC_PRODUCER_WARP) {
         tmem_alloc(tmem_ptr_smem, 512);
@@ -309,14 +420,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
         // issues.  tcgen05.commit tracks the MMAs of the issuing thread, so the same lane must issue both: elect.sync
         // picks the same lane every time for a full mask.
         const int mt = warp - ATC_MMA_WARP0;
-        constexpr uint32_t idesc_s = umma_idesc_bf16(128, TK);
+        constexpr uint32_t idesc_s = umma_idesc_f16(128, TK);  // q and k arrive as f16
         constexpr uint32_t idesc_o = umma_idesc_f16_bmn(128, 64);
         const uint32_t t_tile = __shfl_sync(0xffffffffu, tmem_base, 0) + 256 * mt;
         constexpr int nk = TK >> 4;
         constexpr int ka = (nk + 1) / 2;  // k-steps whose keys belong to the first half of the row
         const uint32_t smem_base = smem_u32(smem);
-        // start tile 1 half an item late: its MMAs / epilogue then fall into tile 0's softmax and vice versa
-        if (mt == 1) mbar_wait(&p_full[0], 0);
         int it = 0;
         for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
             const int b = it & 1;
@@ -368,12 +477,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                 uint8_t* set = smem + b * set_bytes;
                 mbar_wait(&qk_full[b], (it >> 1) & 1);
                 if (rtid == 0) ATC_STAMP(16);
-                for (int u = rtid; u < units; u += ATC_ROT_WARPS * 32) {
-                    const int ridx = u >> 2, cpair = u & 3;
-                    const int isk = ridx >= nrot;
-                    const int tok = p.prefix + ridx - (isk ? nrot : 0);
-                    atc_rope_unit(isk ? set + 32768 : set, tok, cpair, rope_tab + (tok - p.prefix) * 32);
-                }
+                // query tile 1 follows tile 0 in the set: a query row's offset is tok * 128 in both tiles
+                for (int u0 = rtid; u0 < units; u0 += 4 * ATC_ROT_WARPS * 32)
+                    atc_rope_units_f16<4>(set, set + 32768, u0, ATC_ROT_WARPS * 32, units, nrot, p.prefix, rope_tab);
                 fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&qk_ready[b]);
@@ -391,8 +497,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
         const uint32_t t_row = tmem_base + 256 * mt + (uint32_t(quarter * 32) << 16);
         const float c = p.scale_log2;
         constexpr int CA = ((TK >> 4) + 1) / 2 * 16;  // keys [0,CA) for half 0, [CA,TK) for half 1 (multiples of 16)
-        float* my_max = xchg + ((0 * 2 + mt) * 2 + half) * 128 + rit;
-        float* peer_max = xchg + ((0 * 2 + mt) * 2 + (half ^ 1)) * 128 + rit;
         float* my_sum = xchg + ((1 * 2 + mt) * 2 + half) * 128 + rit;
         float* peer_sum = xchg + ((1 * 2 + mt) * 2 + (half ^ 1)) * 128 + rit;
         const bool stamper = (threadIdx.x & 255) == 0;  // first thread of each query tile
@@ -400,14 +504,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
         int it = 0;
         for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
             const int f = w / p.heads, h = w % p.heads;
+            // The two query tiles take turns in the softmax: tile 1 starts item i only when tile 0 has handed over its
+            // P of item i, tile 0 starts item i+1 when tile 1 has handed over item i.  One tile's S / P V MMAs, TMEM drain
+            // and stores then always fall into the other tile's exponentials instead of both tiles queueing for the
+            // MUFU at the same time and idling together afterwards.  (No phase can be skipped: a tile cannot complete
+            // its next P hand-over before every warp of the other tile has seen this one.)
+            if (mt == 1) mbar_wait(&p_full[0], it & 1);
+            else if (it > 0) mbar_wait(&p_full[1], (it - 1) & 1);
             mbar_wait(&s_full[mt], it & 1);
             tc_fence_after();
             if (stamper) ATC_STAMP(sbase);
             float sum = 0.f;
             if (warp_has_rows) {  // the partner warp (same rows) takes the same branch
                 const int bar_id = 1 + mt * 4 + quarter;
-                if (half == 0) sum = atc_softmax_range<TK, 0, CA>(t_row, T, c, my_max, peer_max, bar_id);
-                else sum = atc_softmax_range<TK, CA, TK>(t_row, T, c, my_max, peer_max, bar_id);
+                const uint32_t xmax0 = smem_u32(xchg + ((0 * 2 + mt) * 2 + 0) * 128 + rit);
+                if (half == 0) sum = atc_softmax_range<TK, 0, CA, 2>(t_row, T, c, xmax0, 0, bar_id);
+                else sum = atc_softmax_range<TK, CA, TK, 2>(t_row, T, c, xmax0, 1, bar_id);
             }
             *my_sum = sum;  // read by the partner thread after o_full (ordered through the mbarrier chain)
             tc_fence_before();

@@ -143,6 +143,10 @@ int launch_attention_tc_tk(const CUtensorMap& tq, const CUtensorMap& tkv, const 
     return check_cuda(cudaGetLastError(), "attention_tc_kernel launch");
 }
 
+// does the tcgen05 attention take q and k as IEEE f16 (like v) for this geometry?  The one-tile-per-128-rows kernel
+// (T <= 256) does: its RoPE prologue and logits run on f16 operands; the key-split kernel keeps bf16 q and k.
+bool attention_qk_f16(int T) { return ((T + 15) & ~15) <= 256; }
+
 // cs/sn: RoPE tables applied in the kernel's prologue, or null when q and k arrive rotated (EPI_QKV_ROPE_BF16)
 int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* cs, const float* sn, int frames,
                         int T, int prefix, int heads, cudaStream_t s) {
@@ -396,7 +400,9 @@ int encoder_layer_unfused(cbas_encoder* e, int li, int n, cudaStream_t s, bool c
     const float* bqkv = (const float*)L.b_qkv;
     GemmParams p{};
     if (!cls_only) {
-        p.M = M; p.N = 3 * D; p.K = D; p.bias = bqkv; p.out = e->qkv; p.ldo = 3 * D; p.f16_from = 2 * D;
+        // V is stored as f16 for the tcgen05 kernels; the T <= 256 kernel takes q and k as f16 as well
+        p.M = M; p.N = 3 * D; p.K = D; p.bias = bqkv; p.out = e->qkv; p.ldo = 3 * D;
+        p.f16_from = attention_qk_f16(T) ? 0 : 2 * D;
         if (int rc = launch_gemm(e->hb, D, wqkv, D, p, tc ? EPI_BIAS_BF16_VF16 : EPI_BIAS_BF16, s, PROF_QKV_GEMM)) return rc;
         if (tc) {
             if (int rc = launch_attention_tc(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n, T,
@@ -450,8 +456,9 @@ int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
     // norm1 + QKV projection (HF :433-434, :305-311)
     GemmParams p = ln_consumer(e, M, 3 * D, L.c1_qkv, L.b_qkv, e->qkv, 3 * D, e->stats[0], 1);
     if (use_attention_tc(e->attention_impl, e->T, c.prefix_tokens, e->w.rope_cos != nullptr)) {
-        // V stored as f16; the tcgen05 attention kernel rotates q and k in its prologue
-        p.f16_from = 2 * D;
+        // V stored as f16 (q and k too for frames of at most 256 tokens); the attention kernel rotates q and k in
+        // its prologue
+        p.f16_from = attention_qk_f16(e->T) ? 0 : 2 * D;
         if (int rc = launch_gemm(e->hb, D, (const __nv_bfloat16*)L.w_qkv, D, p, EPI_BIAS_BF16_VF16, s, PROF_QKV_GEMM))
             return rc;
         if (int rc = launch_attention_tc(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n,
@@ -672,6 +679,8 @@ int cbas_b200_attention_tc(const void* qkv_bf16_dev, void* out_bf16_dev, const f
     return launch_attention_tc((const __nv_bfloat16*)qkv_bf16_dev, (__nv_bfloat16*)out_bf16_dev, rope_cos_dev,
                                rope_sin_dev, frames, T, prefix, heads, (cudaStream_t)stream);
 }
+
+int cbas_b200_attention_tc_qk_f16(int32_t T) { return attention_qk_f16(T) ? 1 : 0; }
 
 int cbas_b200_debug_attention_trace(void* trace_dev) {
     g_attention_trace = (long long*)trace_dev;

@@ -383,6 +383,15 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -410,6 +419,10 @@ __device__ __forceinline__ uint32_t ex2_approx_f16x2(uint32_t x) {
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
     __half2 v = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+// kind::f16 instruction descriptor with f16 (not bf16) A and B, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 // kind::f16 instruction descriptor with f16 (not bf16) A and B, B MN-major
 __host__ __device__ constexpr uint32_t umma_idesc_f16_bmn(uint32_t M, uint32_t N) {

@@ -142,6 +142,10 @@ int cbas_b200_gemm_resid_ln(const void* a_dev, const void* w_dev, const float* b
 int cbas_b200_gemm_ln_a(const void* hb_dev, const float* stats_dev, const void* w_folded_dev, const float* c1_dev,
                         const float* c2_dev, void* out_bf16_dev, int32_t M, int32_t N, int32_t K, int32_t epi,
                         float eps, void* stream);
+/* Operand format of cbas_b200_attention_tc: 1 = the q and k thirds of the fused QKV activation are IEEE f16 like the
+ * v third (frames of at most 256 tokens: the kernel's RoPE prologue and logits run on f16 operands - the reference runs
+ * the block under fp16 autocast, cbas.py:433), 0 = q and k are bf16 and only v is f16 (the key-split kernel). */
+int cbas_b200_attention_tc_qk_f16(int32_t T);
 /* Profiling aid (per host thread): device buffer of 64*16 int64 that CTA 0 of the tcgen05 attention kernel fills with
  * clock64() stamps per pipeline stage (null switches it off). */
 int cbas_b200_debug_attention_trace(void* trace_dev);

@@ -54,14 +54,16 @@ def test_attention_with_rope(side, heads, frames):
     assert e < 1.5e-2, f"attention rel err {e}"
 
 
-def _qkv_with_f16_v(frames, T, D, heads):
-    """QKV buffer as the encoder's GEMM lays it out for the tcgen05 kernel: q, k bf16; v IEEE f16 bits.
-    Returns the buffer and the exact values it encodes as [3, B, H, T, 64] fp32."""
+def _qkv_with_f16_v(frames, T, D, heads, prefix=0, rope=False):
+    """QKV buffer as the encoder's GEMM lays it out for the tcgen05 kernels: v IEEE f16 bits; q, k bf16, or f16 as well
+    where cbas_b200_attention_tc_qk_f16 says so (frames of at most 256 tokens).  Returns the buffer and the exact
+    values it encodes as [3, B, H, T, 64] fp32."""
     raw = torch.randn(frames * T, 3 * D, device="cuda") * 1.5
     qkv = raw.to(torch.bfloat16)
-    v16 = raw[:, 2 * D:].to(torch.float16)
-    qkv.view(torch.int16)[:, 2 * D:] = v16.view(torch.int16)
-    vals = torch.cat([qkv[:, :2 * D].float(), v16.float()], dim=1)
+    f16_from = 0 if _lib.lib().cbas_b200_attention_tc_qk_f16(T) else 2 * D
+    x16 = raw[:, f16_from:].to(torch.float16)
+    qkv.view(torch.int16)[:, f16_from:] = x16.view(torch.int16)
+    vals = torch.cat([qkv[:, :f16_from].float(), x16.float()], dim=1)
     return qkv, vals.view(frames, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
 
 
@@ -83,13 +85,13 @@ def test_attention_tcgen05_rope_prologue(side, heads, frames):
     T, P, D = n * n + 5, 5, heads * 64
     cos, sin = rope_tables(n, n)
     cos, sin = cos.cuda(), sin.cuda()
-    qkv, x = _qkv_with_f16_v(frames, T, D, heads)
+    qkv, x = _qkv_with_f16_v(frames, T, D, heads, P, True)
     out = attention_tc(qkv, frames, T, heads, cos, sin, P).float()
     q, k = _rope_ref(x[0], x[1], cos, sin)
     want = F.scaled_dot_product_attention(q, k, x[2], scale=0.125).permute(0, 2, 1, 3).reshape(frames * T, D)
     e = rel_err(out, want)
     assert e < 1.5e-2, f"tcgen05 attention + RoPE prologue rel err {e}"
-    qkv_bf = torch.cat([qkv[:, :2 * D], x[2].permute(0, 2, 1, 3).reshape(frames * T, D).to(torch.bfloat16)], dim=1)
+    qkv_bf = x.permute(1, 3, 0, 2, 4).reshape(frames * T, 3 * D).to(torch.bfloat16)
     legacy = attention(qkv_bf.contiguous(), cos, sin, frames, T, P, heads).float()  # the mma.sync kernel, bf16 V
     assert rel_err(out, legacy) < 1.5e-2
 
@@ -100,7 +102,7 @@ def test_attention_tcgen05_key_split(T, heads, frames, rope_side):
     """257..384 tokens per frame (256-px frames; DINOv2-with-registers): the key-split kernel merges two partial
     softmaxes per query tile; with and without the RoPE prologue, vs torch SDPA and vs the mma.sync kernel."""
     P, D = 5, heads * 64
-    qkv, x = _qkv_with_f16_v(frames, T, D, heads)
+    qkv, x = _qkv_with_f16_v(frames, T, D, heads, P, bool(rope_side))
     if rope_side:
         assert rope_side * rope_side + P == T
         cos, sin = rope_tables(rope_side, rope_side)
@@ -127,7 +129,7 @@ def test_attention_every_token_count_residue(impl):
         for T in [6, 17, 31, 64, 100, 127, 128, 129, 143, 160, 177, 191, 206, 222, 239, 255, 256, 257, 270, 288, 303,
                   319, 336, 350, 367, 384, 385, 430, 512, 592]:
             for with_rope in (False, True):
-                qkv, x = _qkv_with_f16_v(frames, T, D, heads)
+                qkv, x = _qkv_with_f16_v(frames, T, D, heads, P, with_rope)
                 if with_rope:
                     ang = torch.rand(T - P, 32, device="cuda") * 6.28
                     cos, sin = torch.cos(ang).contiguous(), torch.sin(ang).contiguous()
@@ -136,9 +138,10 @@ def test_attention_every_token_count_residue(impl):
                     cos = sin = None
                     q, k = x[0], x[1]
                 if impl == 1 or not _lib.lib().cbas_b200_attention_tc_supported(T, P, 1 if with_rope else 0):
-                    vb = x[2].permute(0, 2, 1, 3).reshape(frames * T, D).to(torch.bfloat16)
-                    buf = torch.cat([qkv[:, :2 * D], vb], dim=1).contiguous()
-                    v_ref = vb.float().view(frames, T, heads, 64).permute(0, 2, 1, 3)
+                    buf = x.permute(1, 3, 0, 2, 4).reshape(frames * T, 3 * D).to(torch.bfloat16).contiguous()
+                    xb = buf.float().view(frames, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+                    q, k = _rope_ref(xb[0], xb[1], cos, sin) if with_rope else (xb[0], xb[1])
+                    v_ref = xb[2]
                     out = attention(buf, cos, sin, frames, T, P, heads).float()
                 else:
                     v_ref = x[2]

@@ -12,7 +12,7 @@ frames = int(sys.argv[3]) if len(sys.argv) > 3 else 512
 heads = 12
 side = {201: 14, 261: 16}.get(T)
 cos, sin = rope_tables(side, side); cos, sin = cos.cuda(), sin.cuda()
-qkv = torch.randn(frames * T, 3 * heads * 64, device="cuda").to(torch.bfloat16)
+qkv = torch.randn(frames * T, 3 * heads * 64, device="cuda").to(torch.float16).view(torch.bfloat16)  # f16 bits (q4 kernel operands)
 for _ in range(3): attention_tc(qkv, frames, T, heads, cos, sin, 5)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
