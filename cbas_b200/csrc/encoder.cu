@@ -20,7 +20,7 @@
 using namespace cbas;
 
 #ifndef CBAS_LN_FUSED_DEFAULT
-#define CBAS_LN_FUSED_DEFAULT 1
+#define CBAS_LN_FUSED_DEFAULT 0
 #endif
 
 namespace {

@@ -22,10 +22,17 @@ def attention_impl(request):
     return request.param
 
 
+def _centred_cosine(got, want):
+    """Cosine after removing the frame-independent part (the mean oracle row): with random-init weights the plain
+    cosine is ~1 whatever the input, this one measures the input-dependent component."""
+    got, want = torch.as_tensor(got).double(), torch.as_tensor(want).double()
+    return cosine_rows(got - want.mean(0), want - want.mean(0)).min().item()
+
+
 def _report(tag, got, want):
     got, want = torch.as_tensor(got).double(), torch.as_tensor(want).double()
     cos = cosine_rows(got, want).min().item()
-    cc = cosine_rows(got - want.mean(0), want - want.mean(0)).min().item()
+    cc = _centred_cosine(got, want)
     rel = rel_err(got, want)
     # input dependence (SURVEY H4): every GPU row must be nearest to ITS OWN oracle row, not to another frame's
     dist = torch.cdist(got, want)
@@ -34,9 +41,45 @@ def _report(tag, got, want):
     return cos, nn_ok, rel
 
 
-@pytest.mark.parametrize("arch,side,n,scale", [("vits16", 64, 5, 4.0), ("vitb16", 224, 4, 3.0), ("vitb16", 256, 3, 1.0),
-                                              ("vitl16", 96, 3, 2.0)])
-def test_reference_mode_parity(arch, side, n, scale, attention_impl):
+@torch.no_grad()
+def _eager_autocast(model, frames, dtype, mode="reference", size=224):
+    """The reference's own CUDA path (cbas.py:433-435): the same HF model on this GPU under torch.autocast, fp32 pixel
+    values in, CLS row out.  dtype float16 is the reference's numerics of record (autocast's CUDA default), bfloat16
+    the same path with the operand type BASELINE.json prescribes for this build."""
+    m = model.to("cuda")
+    try:
+        x = (oenc.preprocess_reference(frames) if mode == "reference" else oenc.preprocess_processor(frames, size)).cuda()
+        with torch.autocast(device_type="cuda", dtype=dtype):
+            out = m(x).last_hidden_state[:, 0, :]
+        return out.float().cpu()
+    finally:
+        model.to("cpu")
+
+
+def _assert_centred(tag, got, want, model, frames, floor, mode="reference", size=224):
+    """Gate on the input-dependent component of the embedding: mean-centred cosine >= `floor`, and its shortfall from 1
+    at most twice (plus 1e-3) what torch-eager autocast with the SAME operand type (bf16) loses against the same fp32
+    oracle - i.e. the loss is the 8-bit mantissa of the operands, not a defect of these kernels.  The fp16-autocast
+    figure (the reference's own CUDA numerics, 11-bit mantissa) is printed next to it."""
+    cc = _centred_cosine(got, want)
+    cc_bf16 = _centred_cosine(_eager_autocast(model, frames, torch.bfloat16, mode, size), want)
+    cc_fp16 = _centred_cosine(_eager_autocast(model, frames, torch.float16, mode, size), want)
+    print(f"[parity] {tag}: mean-centred cosine ours {cc:.6f} | torch-eager autocast bf16 {cc_bf16:.6f}, fp16 {cc_fp16:.6f}")
+    assert cc >= floor, f"{tag}: mean-centred cosine {cc}"
+    assert (1.0 - cc) <= 2.0 * (1.0 - cc_bf16) + 1e-3, \
+        f"{tag}: centred error {1 - cc:.3e} vs torch-eager bf16 autocast {1 - cc_bf16:.3e}"
+
+
+# last column: floor of the mean-centred cosine.  With 8-bit-mantissa (bf16) operands the input-dependent part of a
+# random-init embedding - a few percent of its norm - carries the rounding noise of twelve or twenty-four blocks:
+# measured here 0.994 / 0.966 / 0.825 / 0.974 / 0.894 against 0.993 / 0.960 / 0.774 / 0.966 / 0.860 for torch-eager bf16
+# autocast of the same model on the same GPU (and 0.9999 / 0.9994 / 0.995 / 0.9994 / 0.998 for fp16 autocast, the
+# reference's own 11-bit-mantissa numerics).  The floors sit just under the measured values; the bound relative to
+# torch-eager bf16 inside _assert_centred is the gate that says "operand rounding, not a kernel defect".
+@pytest.mark.parametrize("arch,side,n,scale,cc_floor", [("vits16", 64, 5, 4.0, 0.99), ("vitb16", 224, 4, 3.0, 0.955),
+                                                       ("vitb16", 256, 3, 1.0, 0.78), ("vitl16", 96, 3, 2.0, 0.965),
+                                                       ("vitl16", 224, 2, 2.0, 0.87)])
+def test_reference_mode_parity(arch, side, n, scale, cc_floor, attention_impl):
     from cbas_b200 import _lib
     if attention_impl >= 2 and not _lib.lib().cbas_b200_attention_tc_supported((side // 16) ** 2 + 5, 5, 1):
         pytest.skip("no tcgen05 attention kernel for this token count")
@@ -57,6 +100,7 @@ def test_reference_mode_parity(arch, side, n, scale, attention_impl):
     cos, nn_ok, rel = _report(f"{arch}@{side} reference-mode", got, want)
     assert cos >= 0.999 and rel <= 2e-2
     assert nn_ok
+    _assert_centred(f"{arch}@{side}", got, want, model, frames, cc_floor)
     # float-plane entry (DinoEncoder.__call__ contract, cbas.py:435,672)
     x = torch.from_numpy(frames[:, :, :, 1] / 255.0).float().unsqueeze(1)
     got2 = enc(x).squeeze(1).cpu()
@@ -64,14 +108,18 @@ def test_reference_mode_parity(arch, side, n, scale, attention_impl):
     assert rel_err(got2, got) < 1e-5
 
 
-def test_processor_mode_parity():
+@pytest.mark.parametrize("n", [4, 24], ids=["single_cta_gemms", "cta_pair_gemms"])
+def test_processor_mode_parity(n):
+    """BASELINE configs[1] geometry (256-px clip -> HF processor -> ViT-B/16 at 224 px) against the fp32 oracle; 24
+    frames = 4 824 token rows take the CTA-pair GEMM tiles the 512-frame production chunk runs on."""
     model = oenc.build_hf_model("vitb16", seed=1, init_scale=3.0)
-    frames = oenc.synthetic_frames(4, 256, 256, seed=6)
+    frames = oenc.synthetic_frames(n, 256, 256, seed=6)
     want = oenc.encode(model, frames, mode="processor", size=224)
-    enc = DinoEncoder.from_hf_model(model, "cuda", preprocess="processor", image_size=224, max_frames=8)
+    enc = DinoEncoder.from_hf_model(model, "cuda", preprocess="processor", image_size=224, max_frames=24)
     got = enc.encode_u8(torch.from_numpy(frames).cuda()).cpu()
-    cos, nn_ok, rel = _report("vitb16 processor 256->224", got, want)
+    cos, nn_ok, rel = _report(f"vitb16 processor 256->224, {n} frames", got, want)
     assert cos >= 0.999 and rel <= 2e-2 and nn_ok
+    _assert_centred(f"vitb16 processor, {n} frames", got, want, model, frames, 0.998, mode="processor", size=224)
 
 
 @pytest.mark.parametrize("arch,side,n,layers,trained_px", [
@@ -132,11 +180,14 @@ def test_against_reference_encode_file_fixture(golden_dir):
     assert cos >= 0.999 and rel <= 2e-2 and nn_ok
 
 
-def test_rows_whose_mean_dwarfs_their_spread():
-    """norm1 / norm2 are fused into the GEMMs around them and the QKV / up GEMMs read a bf16 copy of the residual
-    stream; that copy is shifted by the row's previous mean precisely so that this case keeps its accuracy: every token
-    row sits at a mean of ~40 with a spread of ~1 (embedding bias and prefix tokens shifted), and every residual update
-    moves the row mean again (o_proj / down_proj biases shifted).  Same gates as the ordinary parity test."""
+@pytest.mark.parametrize("ln_fusion", [0, 1], ids=["standalone_layernorm", "fused_layernorm"])
+def test_rows_whose_mean_dwarfs_their_spread(ln_fusion):
+    """Every token row sits at a mean of ~40 with a spread of ~1 (embedding bias and prefix tokens shifted), and every
+    residual update moves the row mean again (o_proj / down_proj biases shifted).  The standalone LayerNorm kernels
+    (default) take their statistics from the fp32 residual stream; with CBAS_OPT_LN_FUSION the QKV / up GEMMs read a
+    bf16 copy of it, shifted by the row's previous mean precisely so that this case keeps its accuracy.  Same gates
+    as the ordinary parity test, both ways."""
+    from cbas_b200 import _lib
     model = oenc.build_hf_model("vitb16", seed=2, init_scale=3.0)
     with torch.no_grad():
         model.embeddings.patch_embeddings.bias += 40.0
@@ -148,6 +199,7 @@ def test_rows_whose_mean_dwarfs_their_spread():
     frames = oenc.synthetic_frames(4, 224, 224, seed=12)
     want = oenc.encode(model, frames, mode="reference")
     enc = DinoEncoder.from_hf_model(model, "cuda", max_frames=8)
+    enc.set_option(_lib.OPT_LN_FUSION, ln_fusion)
     fd = torch.from_numpy(frames).cuda()
     hs = oenc.hidden_states(model, oenc.preprocess_reference(frames))
     print(f"[parity] large-mean rows: row mean {float(hs[1].mean(-1).abs().min()):.1f}.., spread {float(hs[1].std(-1).max()):.2f} max")
@@ -163,8 +215,8 @@ def test_rows_whose_mean_dwarfs_their_spread():
 
 @pytest.mark.parametrize("arch,side,n", [("vitb16", 224, 6), ("vits16", 256, 24), ("vitl16", 96, 3)])
 def test_fused_layernorm_matches_standalone_layernorm(arch, side, n):
-    """norm1 / norm2 inside the GEMM epilogues against the same encoder with standalone LayerNorm kernels between the
-    GEMMs (the round-1 arrangement): same weights, same function, different rounding points."""
+    """norm1 / norm2 inside the GEMM epilogues (CBAS_OPT_LN_FUSION 1) against the same encoder with standalone
+    LayerNorm kernels between the GEMMs (the default): same weights, same function, different rounding points."""
     from cbas_b200 import _lib
     enc = DinoEncoder(f"synthetic:{arch}@4", "cuda", max_frames=24)
     frames = torch.from_numpy(oenc.synthetic_frames(n, side, side, seed=13)).cuda()
