@@ -78,7 +78,10 @@ def executed_work(a, side, n, preprocess, pruned=True):
         },
         "bytes": {
             "preprocess": n * (side * side * 3 if preprocess != "processor" else SRC_HW[0] * SRC_HW[1] * 3) + n * Np * Kp * 2.0,
-            "layernorm": M * D * (4 + 2.0),   # the one statistics pass after the embedding: h in, shifted bf16 copy out
+            # standalone norm1 / norm2 kernels (the default): fp32 h in, bf16 out, two per full block, norm1 over every
+            # row + norm2 over the CLS rows in the pruned last block
+            "layernorm": (2 * full + last) * M * D * (4 + 2.0) + last * n * D * (4 + 2.0),
+            "layernorm_fused": M * D * (4 + 2.0),  # CBAS_B200_LN_FUSION=1: only the statistics pass after the embedding
             "final_ln": n * D * (4 + 4.0),
         },
     }
@@ -493,7 +496,8 @@ def main():
             tf = work["flops"][k] / sec / 1e12
             e.update({"tflops_executed": tf, "frac_of_sustained": tf / peaks["tf_sustained"], "frac_of_burst": tf / peaks["tf_burst"]})
         elif k in work["bytes"]:
-            gbs = work["bytes"][k] / sec / 1e9
+            by = work["bytes"]["layernorm_fused"] if k == "layernorm" and v[1] / K < 3 else work["bytes"][k]
+            gbs = by / sec / 1e9
             e.update({"gbs_algorithmic": gbs, "frac_of_hbm": gbs / peaks["hbm"]})
         breakdown[k] = e
     dom = max(prof, key=lambda k: prof[k][0])

@@ -155,6 +155,29 @@ class VideoReader:
             self._cap.release()
 
 
+class _SpanReader:
+    """Frames [start, stop) of another reader behind the same three calls (len, get_batch, read_into): what one rank
+    sees of a long video that several GPUs encode together (parallel.split_frame_range)."""
+
+    def __init__(self, reader, start: int, stop: int):
+        n = len(reader)
+        if not 0 <= start <= stop <= n:
+            raise ValueError(f"frame range [{start}, {stop}) outside the video's {n} frames")
+        self._r, self._start, self._stop = reader, int(start), int(stop)
+        self.frame_hw = getattr(reader, "frame_hw", None)
+        if hasattr(reader, "read_into"):
+            self.read_into = lambda s, e, out: reader.read_into(self._start + s, self._start + e, out)
+
+    def __len__(self) -> int:
+        return self._stop - self._start
+
+    def get_batch(self, indices):
+        return self._r.get_batch([self._start + int(i) for i in indices])
+
+    def close(self):
+        self._r.close()
+
+
 _COPY_THREADS = max(1, min(4, (os.cpu_count() or 1) // 2))
 _pool = None
 
@@ -180,12 +203,16 @@ def _make_pipeline(encoder, frame_hw: Tuple[int, int], planes: bool = False):
     return pipe
 
 
-def encode_file(encoder, path: str, progress_callback: Optional[Callable[[float], None]] = None) -> Optional[str]:
+def encode_file(encoder, path: str, progress_callback: Optional[Callable[[float], None]] = None, *,
+                frame_range: Optional[Tuple[int, int]] = None, out_path: Optional[str] = None) -> Optional[str]:
     """Encode a video into `<video>_cls.h5` (cbas.py:399-456).
 
     Returns the output path, or None for a video with no frames; decode, I/O and compute errors are raised after
     the `.tmp` file has been removed.  The finished file appears atomically (os.replace).  `progress_callback`
-    receives the percentage after each 512-frame chunk has been decoded, from the calling thread."""
+    receives the percentage after each 512-frame chunk has been decoded, from the calling thread.
+
+    Beyond the reference's signature (keyword-only, for one long video on several GPUs - launch.py --split-video):
+    `frame_range=(start, stop)` encodes only those frames, `out_path` names the file they go to."""
     if not isinstance(encoder, DinoEncoder):
         raise TypeError("cbas_b200.encode_file needs a cbas_b200.DinoEncoder (there is no PyTorch fallback path)")
     # decoder errors propagate, as in the reference (cbas.py:400-402)
@@ -197,12 +224,19 @@ def encode_file(encoder, path: str, progress_callback: Optional[Callable[[float]
                                      chunk=CHUNK_SIZE, green_only=green_only)
     else:
         reader = VideoReader(path)
+    if frame_range is not None:
+        try:
+            reader = _SpanReader(reader, frame_range[0], frame_range[1])
+        except Exception:
+            reader.close()
+            raise
     video_len = len(reader)
     if video_len == 0:
         print(f"Warning: Video {path} contains no frames. Skipping.")
+        reader.close()
         return None
 
-    out_file_path = os.path.splitext(path)[0] + "_cls.h5"
+    out_file_path = out_path or (os.path.splitext(path)[0] + "_cls.h5")
     tmp_file_path = out_file_path + ".tmp"
     writer = None
     try:
@@ -261,6 +295,11 @@ def encode_file(encoder, path: str, progress_callback: Optional[Callable[[float]
 
 
 # ----------------------------------------------------------------------------------------------- infer
+# frames classified per read of the `_cls.h5` file (the reference streams 20 000 at a time to bound host memory,
+# cbas.py:482; a B200 wants longer launches: 262 144 ViT-B rows are 0.4 GB of f16 on the host and on the device)
+INFERENCE_CHUNK_SIZE = 262144
+
+
 def _as_native_head(model, device: torch.device) -> ClassifierLSTMDeltas:
     """Accept our head, or the reference's `classifier_head.ClassifierLSTMDeltas` instance (same state_dict)."""
     if isinstance(model, ClassifierLSTMDeltas):
@@ -299,17 +338,29 @@ def infer_file(file_path: str, model, dataset_name: str, behaviors: List[str], s
             raise ValueError(f"seq_len {seq_len} does not match the model's window ({head.seq_len})")
         if len(behaviors) != head.out_features:
             raise ValueError("behaviors does not match the model's output width")
+        half = seq_len // 2
         with store.EmbeddingReader(file_path) as f:
             total_frames = f.shape[0]
             if total_frames == 0:
                 print(f"Warning: HDF5 file {file_path} is empty.")
                 return None
-            emb = np.ascontiguousarray(f.read(0, total_frames))
-        if emb.dtype != np.float16:
-            emb = emb.astype(np.float16)
-        emb_dev = torch.from_numpy(emb).to(device, non_blocking=False)
-        with torch.no_grad():
-            probs = head.infer_embeddings(emb_dev, temperature=float(temperature)).cpu().numpy()
+            # Bounded memory like the reference (cbas.py:482,497-508): INFERENCE_CHUNK_SIZE target frames at a time,
+            # read with +-seq_len//2 frames of context; only the probabilities (a few bytes per frame) accumulate.
+            # infer_embeddings replicate-pads the ends of what it is given, which is the video's own padding for the
+            # first and last chunk and falls on discarded context rows everywhere else.
+            parts = []
+            for start_idx in range(0, total_frames, INFERENCE_CHUNK_SIZE):
+                end_idx = min(start_idx + INFERENCE_CHUNK_SIZE, total_frames)
+                read_start, read_end = max(0, start_idx - half), min(total_frames, end_idx + half)
+                emb = np.ascontiguousarray(f.read(read_start, read_end))
+                if emb.dtype != np.float16:
+                    emb = emb.astype(np.float16)
+                emb_dev = torch.from_numpy(emb).to(device, non_blocking=False)
+                with torch.no_grad():
+                    p_dev = head.infer_embeddings(emb_dev, temperature=float(temperature))
+                parts.append(p_dev[start_idx - read_start:end_idx - read_start].cpu().numpy())
+                del emb_dev, p_dev
+            probs = np.concatenate(parts) if len(parts) > 1 else parts[0]
         if len(probs) != total_frames:
             print(f"Warning: Prediction count ({len(probs)}) != Frame count ({total_frames}).")
         pd.DataFrame(probs, columns=behaviors).to_csv(output_file, index=False)
@@ -318,6 +369,13 @@ def infer_file(file_path: str, model, dataset_name: str, behaviors: List[str], s
         print(f"Error during buffered inference on {file_path}: {e}")
         traceback.print_exc()
         return None
+
+
+# ----------------------------------------------------------------------------------------------- training
+def train_lstm_model(*args, **kwargs):
+    """Head training behind the reference's name and signature (cbas.py:1274-1422); see cbas_b200.training."""
+    from .training import train_lstm_model as _train
+    return _train(*args, **kwargs)
 
 
 # ----------------------------------------------------------------------------------------------- actogram

@@ -6,8 +6,11 @@ reference `model.pth` loads with `load_state_dict`, strict or not, exactly as `w
 (csrc/head.cu).  `infer_embeddings` is the fast path `infer_file` uses: the whole `cls` array in, one
 probability row per frame out, with infer_file's windowing, edge padding and temperature softmax on the GPU.
 
-Inference only: training mode (dropout, autograd) is the reference's job (head training is out of
-scope); calling forward() in train mode raises.
+Eval mode is the product path (the native kernels, no autograd).  In train mode (`model.train()`, used only by
+`cbas_b200.training.train_lstm_model`) forward() is a differentiable restatement of the same function
+in torch ops on the GPU - dropout, autograd and the cuDNN LSTM are library code there, on purpose: the gradient step
+is not on the streamed encode / inference path this library accelerates, while every evaluation pass of a training
+run and the model it returns go through the native kernels again.
 """
 from __future__ import annotations
 
@@ -53,9 +56,72 @@ class ClassifierLSTMDeltas(nn.Module):
         self.lstm = nn.LSTM(256, lstm_hidden_size, num_layers=lstm_layers, batch_first=True, bidirectional=True)
         self._native = None
         self._native_key = None
+        self._stream_mats = None
         self.eval()
         for p in self.parameters():
             p.requires_grad_(False)
+
+    def train(self, mode: bool = True):
+        """Training mode switches forward() to the differentiable torch path and makes the parameters trainable;
+        eval() goes back to the native kernels (parameters frozen, as a loaded model.pth is used)."""
+        super().train(mode)
+        for p in self.parameters():
+            p.requires_grad_(bool(mode))
+        return self
+
+    # ---- differentiable path (training only) --------------------------------------------------------------
+    def _time_operators(self, T: int, device, dtype):
+        """The three temporal streams of classifier_head.py:100-116 as constant [T,T] operators on the time axis:
+        S = EMA smoothing (x_s[0] = x[0], x_s[t] = lerp(x_s[t-1], x[t], alpha)), D1 = first difference of the
+        smoothed stream with the two-frame reflected head (delta[0] = x_s[0] - x_s[1]), D2 = second difference
+        (acc[t] = d[t+1] - d[t] over the padded differences)."""
+        key = (T, str(device), dtype)
+        if self._stream_mats is not None and self._stream_mats[0] == key:
+            return self._stream_mats[1]
+        a = float(self.ema_alpha)
+        S = torch.zeros(T, T, dtype=torch.float64)
+        S[0, 0] = 1.0
+        for t in range(1, T):
+            S[t] = (1.0 - a) * S[t - 1]
+            S[t, t] += a
+        # padded sequence p = [x2, x1, x0, x1, ..., x_{T-1}] (reflect) or [x0, x0, x0, x1, ...] (replicate, T < 3)
+        P = torch.zeros(T + 2, T, dtype=torch.float64)
+        head = (2, 1) if T >= 3 else (0, 0)
+        P[0, head[0]] = 1.0
+        P[1, head[1]] = 1.0
+        P[2:] = torch.eye(T, dtype=torch.float64)
+        dP = P[1:] - P[:-1]            # [T+1, T]: all padded first differences
+        D1 = dP[1:]                     # delta stream: the last T of them
+        D2 = dP[1:] - dP[:-1]           # acceleration stream
+        mats = tuple((m @ S if i else S).to(device=device, dtype=dtype) for i, m in enumerate((S, D1, D2)))
+        self._stream_mats = (key, mats)
+        return mats
+
+    def _forward_autograd(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        B, T, _ = x.shape
+        x = x.float()
+        S, D1, D2 = self._time_operators(T, x.device, x.dtype)
+        smooth = torch.einsum("ts,bsf->btf", S, x)
+        delta = torch.einsum("ts,bsf->btf", D1, x)
+        lo, hi = max(0, self.hsl - self.sw), min(T, self.hsl + self.sw + 1)
+        centre = slice(lo, hi) if lo < hi else slice(min(max(0, T // 2), T - 1), min(max(0, T // 2), T - 1) + 1)
+        # linear branch: mean over the centre window of lin1(smoothed frames) (classifier_head.py:118-128)
+        linear_logits = self.lin1(smooth[:, centre]).mean(dim=1)
+        parts = [self.cls_ln(self.cls_bottleneck(smooth)), self.delta_ln(self.delta_bottleneck(delta))]
+        if self.use_acceleration:
+            parts.append(self.acc_ln(self.acc_bottleneck(torch.einsum("ts,bsf->btf", D2, x))))
+        z = self.lin0(torch.cat(parts, dim=-1))
+        z = z - z.mean(dim=1, keepdim=True)
+        out, _ = self.lstm(z)
+        win = out[:, centre]
+        if lo < hi:
+            temp = torch.nn.functional.softplus(self.attention_temp) + 1e-3
+            w = torch.softmax(self.attention_head(win).squeeze(-1) / temp, dim=1).unsqueeze(-1)
+            rawm = (w * win).sum(dim=1)
+        else:
+            rawm = win[:, 0]
+        lstm_logits = self.lin2(rawm)
+        return torch.lerp(linear_logits, lstm_logits, torch.sigmoid(self.gate)), rawm
 
     # ---- native handle management -----------------------------------------------------------------------
     def _apply(self, fn, *a, **k):  # .to() / .cuda() / .float() move the parameters: rebuild the handle lazily
@@ -136,12 +202,15 @@ class ClassifierLSTMDeltas(nn.Module):
 
     # ---- reference-compatible call ------------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """x [B,T,F] -> (final_logits [B,C], rawm [B,2*Hs]); eval mode only."""
-        if self.training:
-            raise NotImplementedError("cbas_b200 head is inference-only; call .eval() (training stays in the reference)")
+        """x [B,T,F] -> (final_logits [B,C], rawm [B,2*Hs]).  Eval mode: the native kernels; train mode: the
+        differentiable torch restatement (see the module docstring)."""
         B, T, Fdim = x.shape
         if T != self.seq_len or Fdim != self.in_features:
             raise ValueError(f"expected windows of [{self.seq_len}, {self.in_features}], got [{T}, {Fdim}]")
+        if self.training:
+            if self.lin1.weight.device.type != "cuda":
+                raise RuntimeError("cbas_b200.ClassifierLSTMDeltas runs on CUDA (sm_100a) only; move it with .to('cuda')")
+            return self._forward_autograd(x.to(self.lin1.weight.device))
         h = self._get_native()
         dev = self.lin1.weight.device
         xd = x.to(device=dev, dtype=torch.float32).contiguous()

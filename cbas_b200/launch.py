@@ -9,6 +9,12 @@ stamped for this encoder, the reference's resume rule, startup_page.py:92-124) a
 `infer_file` on the results (skipping existing CSVs like label_train_page.py:1875-1877).  With `--actogram BEHAVIOUR`
 the per-video bin vectors are summed over all ranks (`parallel.allreduce_bins`: the path's only collective, a few kB)
 and rank 0 prints the group actogram.  Works single-process (no torchrun) as well.
+
+`--split-video` shards WITHIN each video instead (one long recording, N GPUs): every rank encodes a
+contiguous span of the frames (`parallel.split_frame_range`) into `<video>_cls.h5.partRRR`, rank 0 concatenates the
+parts into `<video>_cls.h5`, and each rank classifies its span from that file with +-seq_len//2 rows of context (the
+window of a frame next to a cut reaches into the neighbouring span, cbas.py:503-504); rank 0 collects the probability
+rows (a few bytes per frame) and writes the CSV.  The embeddings travel through the file system, not a collective.
 """
 from __future__ import annotations
 
@@ -24,6 +30,59 @@ import torch
 import torch.distributed as dist
 
 
+def _split_video(path, h5, fresh, enc, head, meta, name, rank, world, dev, args):
+    """One video on `world` ranks: returns (frames this rank encoded or owns, files encoded, files classified)."""
+    from . import cbas, gui_state, parallel, store
+    reader = cbas.VideoReader(path)
+    n = len(reader)
+    reader.close()
+    spans = parallel.split_frame_range(n, world)
+    mine = spans[rank]
+    encoded = 0
+    if not fresh:
+        part = f"{h5}.part{rank:03d}"
+        if len(mine):
+            cbas.encode_file(enc, path, frame_range=(mine.start, mine.stop), out_path=part)
+        dist.barrier()  # every rank's part is on disk
+        if rank == 0:
+            attrs = {"encoder_model_identifier": gui_state.proj.encoder_model_identifier,
+                     "schema_version": store.SCHEMA_VERSION}
+            w = store.EmbeddingWriter(h5 + ".tmp", enc.hidden_size, attrs)
+            for r in range(world):
+                if len(spans[r]):
+                    with store.EmbeddingReader(f"{h5}.part{r:03d}") as pr:
+                        w.append(pr.read(0, pr.shape[0]).astype(np.float32))
+                    os.remove(f"{h5}.part{r:03d}")
+            w.close()
+            os.replace(h5 + ".tmp", h5)
+            encoded = 1
+        dist.barrier()  # the whole file is published
+    classified = 0
+    if head is not None:
+        hp = meta["hyperparameters"]
+        csv = h5.replace("_cls.h5", f"_{name}_outputs.csv")
+        if not os.path.exists(csv):
+            half = int(hp["seq_len"]) // 2
+            ctx = parallel.split_frame_range(n, world, halo=half)[rank]
+            if len(mine):
+                with store.EmbeddingReader(h5) as r:
+                    emb = np.ascontiguousarray(r.read(ctx.start, ctx.stop)).astype(np.float16)
+                temp = float(meta.get("calibration", {}).get("temperature", 1.0))
+                with torch.no_grad():
+                    pr = head.infer_embeddings(torch.from_numpy(emb).to(dev), temperature=temp)
+                probs = pr[mine.start - ctx.start:mine.stop - ctx.start].cpu().numpy()
+            else:
+                probs = np.zeros((0, len(hp["behaviors"])), np.float32)
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object(probs, gathered, dst=0)
+            if rank == 0:
+                import pandas as pd
+                pd.DataFrame(np.concatenate(gathered), columns=hp["behaviors"]).to_csv(csv, index=False)
+                classified = 1
+            dist.barrier()  # the CSV is published
+    return len(mine), encoded, classified
+
+
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--videos", required=True, help="glob of video files (.mp4 / .npy)")
@@ -35,6 +94,8 @@ def main(argv=None) -> int:
     ap.add_argument("--bin-minutes", type=int, default=30)
     ap.add_argument("--threshold", type=float, default=0.5)
     ap.add_argument("--backend", default=None, help="torch.distributed backend (default: nccl, gloo if ranks share a GPU)")
+    ap.add_argument("--split-video", action="store_true",
+                    help="shard the frames of every video across the ranks instead of sharding the videos")
     args = ap.parse_args(argv)
 
     from . import bundle, cbas, gui_state, parallel, store
@@ -55,7 +116,7 @@ def main(argv=None) -> int:
     paths = sorted(glob.glob(args.videos, recursive=True))
     paths = [p for p in paths if not p.endswith("_cls.h5")]
     costs = [float(os.path.getsize(p)) for p in paths]
-    mine = parallel.partition_videos(paths, costs, world)[rank]
+    mine = paths if args.split_video else parallel.partition_videos(paths, costs, world)[rank]
 
     gui_state.proj = types.SimpleNamespace(encoder_model_identifier=args.encoder, path=os.getcwd())
     enc = DinoEncoder(args.encoder, dev, preprocess=args.preprocess)
@@ -73,6 +134,19 @@ def main(argv=None) -> int:
         if os.path.exists(h5):
             with store.EmbeddingReader(h5) as r:
                 fresh = r.attrs.get("encoder_model_identifier") == args.encoder
+        if args.split_video and world > 1:
+            n_mine = _split_video(p, h5, fresh, enc, head, meta, name, rank, world, dev, args)
+            frames += n_mine[0]
+            encoded += n_mine[1]
+            classified += n_mine[2]
+            if args.actogram and head is not None and rank == 0:
+                import pandas as pd
+                hp = meta["hyperparameters"]
+                csv = h5.replace("_cls.h5", f"_{name}_outputs.csv")
+                probs = torch.from_numpy(pd.read_csv(csv)[hp["behaviors"]].to_numpy(dtype=np.float32)).to(dev)
+                b = hp["behaviors"].index(args.actogram)
+                local_bins[p] = actogram_bins(probs, b, args.threshold, int(args.bin_minutes * args.framerate * 60)).cpu()
+            continue
         if not fresh:
             h5 = cbas.encode_file(enc, p)
             encoded += 1

@@ -31,6 +31,12 @@ def log_message(message: str, level: str = "INFO") -> None:
         print(f"[{datetime.now().strftime('%H:%M:%S')}] [{level}] {message}", flush=True)
 
 
+def fit_temperature(model, val_loader, device):
+    """Temperature calibration of a trained head (workthreads.py:103-137); see cbas_b200.training."""
+    from .training import fit_temperature as _fit
+    return _fit(model, val_loader, device)
+
+
 class EncodeThread(threading.Thread):
     def __init__(self, device_str: str = "cuda", progress: Optional[Callable[[dict], None]] = None,
                  poll_seconds: float = 0.2):

@@ -243,3 +243,74 @@ def test_launcher_two_ranks_share_the_work(tmp_path):
     again = run([sys.executable, "-m", "cbas_b200.launch", *common])  # single process, everything already on disk
     assert again["per_rank"][0]["encoded"] == 0 and again["per_rank"][0]["classified"] == 0
     assert again["actogram"]["bins"] == two["actogram"]["bins"] and sum(two["actogram"]["bins"]) > 0
+
+
+def test_launcher_splits_one_long_video_across_two_ranks(tmp_path):
+    """cbas_b200.launch --split-video under torchrun with two ranks (both on GPU 0, gloo): each rank encodes half of
+    the frames, rank 0 concatenates the parts, each rank classifies its span with +-15 frames of context.  The
+    `_cls.h5` must be bit-identical to the single-process file and the CSV equal to the single-process CSV, cut
+    included; nothing but the final artefacts is left on disk."""
+    import json
+    import subprocess
+    import sys
+    import pandas as pd
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    frames = oenc.synthetic_frames(75, 64, 64, seed=77)
+    sd = ohead.make_head_state(384, 4, 128, 64, seed=6)
+    head = ClassifierLSTMDeltas(384, 4, seq_len=31)
+    head.load_state_dict(sd)
+    mdir = str(tmp_path / "models" / "M")
+    bundle.save_model_bundle(mdir, head, "M", ["a", "b", "c", "d"], 31, encoder_model_identifier="synthetic:vits16@4")
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    outs = {}
+    for tag, pre in (("one", [sys.executable]),
+                     ("two", [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29573"])):
+        d = tmp_path / tag
+        d.mkdir()
+        np.save(str(d / "day_00001.npy"), frames)
+        cmd = pre + ["-m", "cbas_b200.launch", "--videos", str(d / "*.npy"), "--encoder", "synthetic:vits16@4",
+                     "--model-dir", mdir, "--actogram", "b", "--framerate", "0.05", "--bin-minutes", "3", "--threshold", "0.0"]
+        if tag == "two":
+            cmd += ["--backend", "gloo", "--split-video"]
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=root, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        rep = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        with store.EmbeddingReader(str(d / "day_00001_cls.h5")) as rd:
+            emb = rd.read(0, rd.shape[0])
+        outs[tag] = (rep, emb, pd.read_csv(str(d / "day_00001_M_outputs.csv")).to_numpy(), sorted(os.listdir(d)))
+    one, two = outs["one"], outs["two"]
+    assert two[0]["world_size"] == 2 and two[0]["frames"] == 75
+    assert [r["frames"] for r in two[0]["per_rank"]] == [38, 37]
+    assert two[1].shape == (75, 384) and np.array_equal(one[1], two[1])
+    assert np.abs(one[2] - two[2]).max() <= 1e-6
+    assert one[3] == two[3], two[3]  # no part files, no .tmp
+    assert one[0]["actogram"]["bins"] == two[0]["actogram"]["bins"]
+
+
+@pytest.mark.parametrize("chunk", [100, 1000, 4096])
+def test_infer_file_streams_the_embedding_file_in_chunks(tmp_path, monkeypatch, chunk):
+    """infer_file reads INFERENCE_CHUNK_SIZE target frames at a time with +-seq_len//2 rows of context (the reference's
+    bounded-memory loop, cbas.py:482,497-508): chunk boundaries - including chunks shorter than the window and a last
+    chunk of one frame - must not show in the CSV, which is checked against one whole-file pass and against the oracle
+    on a sample of frames."""
+    import pandas as pd
+    n = 4097
+    rng = np.random.default_rng(7)
+    emb = (np.cumsum(rng.standard_normal((n, 384)).astype(np.float32) * 0.2, axis=0) % 4.0 - 2.0).astype(np.float16)
+    path = str(tmp_path / "long_cls.h5")
+    w = store.EmbeddingWriter(path, 384, {})
+    w.append(emb.astype(np.float32))
+    w.close()
+    sd = ohead.make_head_state(384, 9, 128, 64, seed=11, scale=2.0)
+    head = ClassifierLSTMDeltas(384, 9, seq_len=31)
+    head.load_state_dict(sd)
+    whole = pd.read_csv(cbas.infer_file(path, head, "whole", BEHAVIORS, 31, device=torch.device("cuda"))).to_numpy()
+    monkeypatch.setattr(cbas, "INFERENCE_CHUNK_SIZE", chunk)
+    got = pd.read_csv(cbas.infer_file(path, head, "chunked", BEHAVIORS, 31, device=torch.device("cuda"))).to_numpy()
+    assert got.shape == whole.shape == (n, 9)
+    assert np.abs(got - whole).max() <= 1e-6 and (got.argmax(1) == whole.argmax(1)).all()
+    sample = np.r_[0:40, chunk - 20:chunk + 20, n - 40:n]
+    sample = sample[(sample >= 0) & (sample < n)]
+    want = ohead.infer_windows(emb, sd, seq_len=31)[sample]
+    assert np.abs(got[sample] - want).max() <= 1e-3

@@ -194,14 +194,35 @@ def test_bundle_round_trip_and_fallbacks(tmp_path):
         bundle.load_model_bundle(d, None, device="cpu")
 
 
-def test_head_is_inference_only_and_cuda_only():
+def test_head_is_cuda_only_in_both_modes():
     m = ClassifierLSTMDeltas(768, 9)
-    assert not m.training
+    assert not m.training and not any(p.requires_grad for p in m.parameters())
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(2, 31, 768))          # no CPU fallback
-    m.train()
-    with pytest.raises(NotImplementedError):
+    m.train()                                # the differentiable path (cbas_b200.training) is GPU-only as well
+    assert all(p.requires_grad for p in m.parameters())
+    with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(2, 31, 768))
+    m.eval()
+    assert not any(p.requires_grad for p in m.parameters())
+
+
+def test_time_operators_reproduce_the_three_streams():
+    """The [T,T] operators of the differentiable head path against a direct statement of classifier_head.py:100-116
+    (EMA, reflected two-frame head, first and second differences), for an ordinary and a two-frame window."""
+    for T in (31, 7, 2, 1):
+        m = ClassifierLSTMDeltas(8, 3, seq_len=T)
+        S, D1, D2 = m._time_operators(T, torch.device("cpu"), torch.float64)
+        x = torch.randn(T, 8, dtype=torch.float64)
+        sm = x.clone()
+        for t in range(1, T):
+            sm[t] = sm[t - 1] + m.ema_alpha * (x[t] - sm[t - 1])
+        head = [sm[2], sm[1]] if T >= 3 else [sm[0], sm[0]]
+        padded = torch.stack(head + list(sm))
+        dx = padded[1:] - padded[:-1]
+        assert torch.allclose(S @ x, sm, atol=1e-12)
+        assert torch.allclose(D1 @ x, dx[1:], atol=1e-12)
+        assert torch.allclose(D2 @ x, dx[1:] - dx[:-1], atol=1e-12)
 
 
 def test_encode_thread_queue_semantics(monkeypatch):
