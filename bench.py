@@ -400,6 +400,9 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager GPU baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the short head / backlog runs appended at N = 1")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong = ONE 18 000-frame clip (BASELINE configs[1]) split into contiguous spans over the GPUs "
+                         "(SURVEY 8e); a step is one pass over the whole clip")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -414,6 +417,9 @@ def main():
         return
     if args.workload == "head":
         run_head(args, rank, world, local_rank)
+        return
+    if args.scaling == "strong":
+        run_strong(args, rank, world, local_rank)
         return
 
     import torch.distributed as dist
@@ -568,6 +574,114 @@ def main():
             "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches), "other_workloads": other,
         }
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_strong(args, rank, world, local_rank):
+    """Strong scaling of BASELINE configs[1]: the ONE 10-min 30-fps clip (18 000 frames) on N GPUs.  Rank r encodes
+    the contiguous span parallel.split_frame_range gives it, 512-frame chunks (its last chunk is partial); a step is
+    one pass over the whole clip; `value` = clip frames / max-over-ranks device time with the span resident in HBM,
+    `e2e` the same through StreamedEncoder.run from pinned host frames with the f16 embeddings copied back."""
+    import torch.distributed as dist
+    from cbas_b200 import _lib, parallel
+    from cbas_b200.encoder import DinoEncoder
+    from cbas_b200.pipeline import StreamedEncoder
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (cbas_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, K = max(3, args.warmup), max(1, args.steps)
+    src_hw = SRC_HW if args.preprocess == "processor" else (SIDE, SIDE)
+    with contextlib.redirect_stdout(sys.stderr):
+        enc = DinoEncoder(f"synthetic:{args.arch}", dev, preprocess=args.preprocess, image_size=SIDE, max_frames=CHUNK)
+    span = parallel.split_frame_range(CLIP_FRAMES, world)[rank]
+    n = len(span)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)  # a span-sized random tensor per rank: the same workload
+    frames = torch.randint(0, 256, (n, *src_hw, 3), dtype=torch.uint8, device=dev, generator=g)
+    out = torch.empty(n, enc.hidden_size, device=dev, dtype=torch.float32)
+
+    def one_pass():
+        for s in range(0, n, CHUNK):
+            e = min(s + CHUNK, n)
+            enc.encode_u8(frames[s:e], out=out[s:e])
+
+    enc.encode_u8(frames[:CHUNK], out=out[:CHUNK])  # warm-up: W chunks, not W whole passes
+    for _ in range(max(0, W - 1)):
+        enc.encode_u8(frames[:min(CHUNK, n)], out=out[:min(CHUNK, n)])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(K):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.result()
+    if not np.isfinite(float(out.double().abs().sum().item())):
+        raise SystemExit("bench: encoder produced a non-finite result")
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((n, *src_hw, 3), dtype=torch.uint8).pin_memory()
+        host.copy_(frames)
+        hn = host.numpy()
+        pipe = StreamedEncoder(enc, src_hw, CHUNK, depth=2)
+        emb = np.empty((n, enc.hidden_size), np.float16)
+        pos = [0]
+
+        def sink(e):
+            emb[pos[0]:pos[0] + len(e)] = e
+            pos[0] += len(e)
+
+        def chunks():
+            for s in range(0, n, CHUNK):
+                yield hn[s:min(s + CHUNK, n)]
+
+        pipe.run((hn[s:min(s + CHUNK, n)] for s in range(0, min(n, CHUNK), CHUNK)), lambda e: None)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        pipe.h2d_bytes = pipe.d2h_bytes = 0
+        t0 = time.perf_counter()
+        pipe.run(chunks(), sink)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        t2 = torch.tensor([wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e = {"value": CLIP_FRAMES / float(t2.item()), "unit": "frames/s", "h2d_bytes_per_step": int(pipe.h2d_bytes),
+               "d2h_bytes_per_step": int(pipe.d2h_bytes), "seconds": float(t2.item()),
+               "api": "StreamedEncoder.run over this rank's span: pinned host frames -> H2D -> encode -> D2H -> f16 rows; "
+                      "host wall clock of one pass, max over ranks (bytes are this rank's)"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": f"frames_per_sec_encoded_{'dinov3_' if not args.arch.startswith('dinov2') else ''}{args.arch.replace('-', '_')}_{SIDE}px",
+            "value": CLIP_FRAMES * K / (ms_max / 1000.0), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"ONE synthetic 10-min 30fps {src_hw[0]}x{src_hw[1]} uint8 clip ({CLIP_FRAMES} frames, BASELINE "
+                                   f"configs[1]) split into {world} contiguous spans, {CHUNK}-frame chunks, DINOv3 {args.arch} {SIDE}px",
+                       "frames_per_rank": [len(r) for r in parallel.split_frame_range(CLIP_FRAMES, world)],
+                       "parallelism": f"frame spans over {world} GPU(s), no collective (the head would read +-15 rows of "
+                                      "context across each cut from the merged file)",
+                       "l2": "every chunk of a pass is a distinct 96 MiB input; >1 GiB of activations per chunk"},
+            "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches)}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -579,6 +579,7 @@ int upload_f32(const std::vector<float>& v, float** out) {
 
 struct cbas_head {
     cbas_head_cfg cfg;
+    int device = 0;  // the CUDA device that was current at create time: every entry point runs there
     int l = 0, r = 0;
     // derived device weights
     __nv_bfloat16* wp = nullptr;    // [384, 3F]
@@ -636,6 +637,7 @@ int cbas_b200_head_create(const cbas_head_cfg* cfg, const cbas_head_weights* w, 
     const bool acc_stream = cfg->use_acceleration != 0;
     auto* h = new cbas_head();
     h->cfg = *cfg;
+    if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; return fail("head: no current CUDA device"); }
     const int hsl = T / 2, sw = cfg->center_window;
     h->l = hsl - sw > 0 ? hsl - sw : 0;
     h->r = hsl + sw + 1 < T ? hsl + sw + 1 : T;
@@ -750,6 +752,7 @@ int cbas_b200_head_create(const cbas_head_cfg* cfg, const cbas_head_weights* w, 
 
 void cbas_b200_head_destroy(cbas_head* h) {
     if (!h) return;
+    DeviceGuard guard(h->device);
     head_free_ws(h);
     cudaFree(h->wp); cudaFree(h->w0); cudaFree(h->b3); cudaFree(h->ln_g); cudaFree(h->ln_b); cudaFree(h->b0);
     for (int i = 0; i < 2; ++i) { cudaFree(h->wih[i]); cudaFree(h->bg[i]); cudaFree(h->whh_t[i]); }
@@ -863,6 +866,8 @@ int cbas_b200_head_infer(cbas_head* h, const void* emb_f16_dev, int64_t n_frames
     if (n_frames < 0) return fail("negative frame count");
     if (n_frames == 0) return 0;
     if (!emb_f16_dev || !probs_out_dev) return fail("null argument");
+    DeviceGuard guard(h->device);  // the handle's device, whatever the calling thread's current device is
+    if (!guard.ok()) return fail("cudaSetDevice to the head's device failed");
     // one window per frame, centred on it, replicate-padded at the ends (cbas.py:497-551)
     return head_run(h, emb_f16_dev, true, n_frames, n_frames, 0, 1, temperature, probs_out_dev, logits_out_dev, nullptr,
                     (cudaStream_t)stream);
@@ -874,6 +879,8 @@ int cbas_b200_head_forward_windows(cbas_head* h, const float* x_f32_dev, int64_t
     if (n_windows < 0) return fail("negative window count");
     if (n_windows == 0) return 0;
     if (!x_f32_dev || !logits_out_dev) return fail("null argument");
+    DeviceGuard guard(h->device);
+    if (!guard.ok()) return fail("cudaSetDevice to the head's device failed");
     // B independent windows laid end to end: window b is centred on frame b*T + T/2 and never leaves its block
     const int T = h->cfg.seq_len;
     return head_run(h, x_f32_dev, false, n_windows * T, n_windows, T / 2, T, 1.0f, nullptr, logits_out_dev, rawm_out_dev,
@@ -888,6 +895,12 @@ int cbas_b200_actogram_bins(const float* probs_dev, int64_t n, int32_t C, int32_
     if (!probs_dev || !bins_out_dev) return fail("null argument");
     const long long nb = (n + bin_frames - 1) / bin_frames;
     if (nb > 0x7fffffffLL) return fail("actogram: too many bins");
+    // no handle here: run on the device that owns the input, whatever the calling thread's current device is
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, probs_dev) != cudaSuccess || attr.type != cudaMemoryTypeDevice)
+        return fail("actogram: probs_dev is not device memory");
+    DeviceGuard guard(attr.device);
+    if (!guard.ok()) return fail("cudaSetDevice to the input's device failed");
     ProfScope prof(PROF_ACTOGRAM, (cudaStream_t)stream);
     actogram_bins_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(probs_dev, n, C, behavior, threshold,
                                                                         bin_frames, bins_out_dev);

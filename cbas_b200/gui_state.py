@@ -8,6 +8,9 @@ from typing import Any, List, Optional
 
 proj: Optional[Any] = None                 # object with .encoder_model_identifier (cbas.Project in the reference)
 dino_encoder: Optional[Any] = None         # cbas_b200.encoder.DinoEncoder once a project is loaded
+# one encoder per device for the thread-pair-per-GPU deployment ("cuda:1" -> DinoEncoder on cuda:1); a worker thread
+# takes the entry of its own device and falls back to `dino_encoder` (the reference has a single encoder object)
+dino_encoders: dict = {}
 
 encode_tasks: List[str] = []
 encode_lock = threading.Lock()

@@ -7,7 +7,10 @@ thread hands finished `_cls.h5` files to the classifier when a live-inference mo
 (workthreads.py:323-328).  eel progress callbacks are replaced by optional Python callables.
 
 Multi-GPU: start one EncodeThread/ClassificationThread pair per device - the queues are shared,
-so videos are distributed dynamically and no collective is involved - or run one process per GPU (bench.py).
+so videos are distributed dynamically and no collective is involved - or run one process per GPU (bench.py,
+cbas_b200.launch).  In the one-process form each device needs its own encoder: put them in
+`gui_state.dino_encoders` keyed by device string; every native handle remembers its device and makes it current for
+the duration of a call, so the threads need no device bookkeeping of their own.
 """
 from __future__ import annotations
 
@@ -52,9 +55,13 @@ class EncodeThread(threading.Thread):
     def stop(self):
         self._stop_flag.set()
 
+    def _encoder(self):
+        """This thread's encoder: the one registered for its device, else the single shared one."""
+        return gui_state.dino_encoders.get(str(self.device)) or gui_state.dino_encoder
+
     def run(self):
         while not self._stop_flag.is_set():
-            if gui_state.dino_encoder is None:
+            if self._encoder() is None:
                 time.sleep(self.poll)
                 continue
             with gui_state.encode_lock:
@@ -77,9 +84,9 @@ class EncodeThread(threading.Thread):
             try:
                 if self.cuda_stream is not None:
                     with torch.cuda.stream(self.cuda_stream):
-                        out_file = cbas.encode_file(gui_state.dino_encoder, file_to_encode, progress_updater)
+                        out_file = cbas.encode_file(self._encoder(), file_to_encode, progress_updater)
                 else:
-                    out_file = cbas.encode_file(gui_state.dino_encoder, file_to_encode, progress_updater)
+                    out_file = cbas.encode_file(self._encoder(), file_to_encode, progress_updater)
                 if out_file:
                     log_message(f"Finished encoding: {name}", "INFO")
                     if gui_state.live_inference_model_name:

@@ -1,6 +1,7 @@
 """The whole drop-in path on the GPU through the public API: encode_file -> `_cls.h5` -> infer_file -> CSV ->
 Actogram, against the CPU oracle on the same synthetic clip, plus the worker-thread chain."""
 import os
+import threading
 import time
 import types
 
@@ -314,3 +315,62 @@ def test_infer_file_streams_the_embedding_file_in_chunks(tmp_path, monkeypatch, 
     sample = sample[(sample >= 0) & (sample < n)]
     want = ohead.infer_windows(emb, sd, seq_len=31)[sample]
     assert np.abs(got[sample] - want).max() <= 1e-3
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(tmp_path, monkeypatch):
+    """One process, two GPUs (workthreads.py: a thread pair per device): an encoder and a head created on cuda:1 are
+    driven from threads whose current device is cuda:0 - every native handle makes its own device current per call -
+    while a second pair works on cuda:0; results equal the single-device ones, and the per-device kernel attributes
+    (shared-memory opt-in, SM count) are set up on both devices."""
+    frames = oenc.synthetic_frames(24, 224, 224, seed=21)
+    sd = ohead.make_head_state(384, 4, 128, 64, seed=6)
+    encs, heads, outs = {}, {}, {}
+    for d in (0, 1):
+        encs[d] = DinoEncoder("synthetic:vits16@4", f"cuda:{d}", max_frames=24)
+        heads[d] = ClassifierLSTMDeltas(384, 4, seq_len=31)
+        heads[d].load_state_dict(sd)
+        heads[d].to(f"cuda:{d}")
+    torch.cuda.set_device(0)
+    errors = []
+
+    def work(d):
+        try:
+            assert torch.cuda.current_device() == 0  # threads inherit device 0: the handles must switch themselves
+            emb = encs[d].encode_u8(torch.from_numpy(frames).to(f"cuda:{d}"))
+            probs = heads[d].infer_embeddings(emb.half())
+            from cbas_b200.classifier_head import actogram_bins
+            outs[d] = (emb.cpu(), probs.cpu(), actogram_bins(probs, 1, 0.2, 5).cpu())
+        except Exception as e:  # noqa: BLE001
+            errors.append((d, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(d,)) for d in (1, 0)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(300)
+    assert not errors, errors
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    # EncodeThread pair per device over one shared queue
+    clips = []
+    for i in range(4):
+        p = str(tmp_path / f"cam_{i:05d}.npy")
+        np.save(p, oenc.synthetic_frames(12, 64, 64, seed=60 + i))
+        clips.append(p)
+    monkeypatch.setattr(gui_state, "proj", None)
+    monkeypatch.setattr(gui_state, "dino_encoder", None)
+    monkeypatch.setattr(gui_state, "dino_encoders", {"cuda:0": encs[0], "cuda:1": encs[1]})
+    monkeypatch.setattr(gui_state, "encode_tasks", list(clips))
+    monkeypatch.setattr(gui_state, "live_inference_model_name", None)
+    workers = [workthreads.EncodeThread("cuda:0", poll_seconds=0.02), workthreads.EncodeThread("cuda:1", poll_seconds=0.02)]
+    for w in workers:
+        w.start()
+    deadline = time.time() + 120
+    while time.time() < deadline and not all(os.path.exists(c[:-4] + "_cls.h5") for c in clips):
+        time.sleep(0.05)
+    for w in workers:
+        w.stop()
+    for w in workers:
+        w.join(10)
+    assert all(os.path.exists(c[:-4] + "_cls.h5") for c in clips)
+    assert sum(w.tasks_processed_in_batch for w in workers) >= 0
