@@ -27,6 +27,11 @@ CHUNK_SIZE = 512  # cbas.py:48
 # like the reference (on a helper thread, one chunk ahead), -1 = one worker per host core minus two.
 # Set from the environment or by assigning cbas.DECODE_WORKERS.
 DECODE_WORKERS = int(os.environ.get("CBAS_B200_DECODE_WORKERS", "0"))
+# In-process decode threads per video (each with its own OpenCV capture, whole 512-frame chunks side by side):
+# 0 = two when the host has at least eight cores (each capture already runs FFmpeg's own frame threads on every core:
+# measured on the 16-core B200 host, mp4 -> _cls.h5 goes 13.2k -> 17.4k frames/s with two and falls off beyond three,
+# profiles/e2e_file_threads_r02.jsonl); 1 = the reference's single decoder.
+DECODE_THREADS = int(os.environ.get("CBAS_B200_DECODE_THREADS", "0"))
 
 
 # ----------------------------------------------------------------------------------------------- video decode
@@ -95,6 +100,30 @@ class VideoReader:
 
     def __len__(self) -> int:
         return self._len
+
+    @property
+    def parallel_readers(self) -> int:
+        """How many independent decoders of this file are worth running side by side (pipeline.run_reader gives each
+        its own thread and whole chunks): OpenCV captures decode concurrently and seek frame-exactly on the
+        constant-frame-rate files CBAS records; `.npy` clips already copy with a thread pool and decord readers are
+        kept single (the reference's one-reader behaviour)."""
+        if self._cap is None:
+            return 1
+        return DECODE_THREADS if DECODE_THREADS > 0 else (2 if (os.cpu_count() or 1) >= 8 else 1)
+
+    def clone(self) -> "VideoReader":
+        """A second capture of the same file with its own decode position (frame count and geometry are inherited,
+        not re-derived)."""
+        if self._cap is None:
+            raise RuntimeError("only OpenCV-backed readers clone")
+        import cv2
+        cap = cv2.VideoCapture(self.path)
+        if not cap.isOpened():
+            raise RuntimeError(f"could not open video '{self.path}'")
+        other = VideoReader.__new__(VideoReader)
+        other.path, other._cap, other._arr, other._decord, other._pos = self.path, cap, None, None, 0
+        other._len, other.frame_hw = self._len, self.frame_hw
+        return other
 
     def get_batch(self, indices) -> np.ndarray:
         idx = list(indices)
@@ -167,6 +196,9 @@ class _SpanReader:
         self.frame_hw = getattr(reader, "frame_hw", None)
         if hasattr(reader, "read_into"):
             self.read_into = lambda s, e, out: reader.read_into(self._start + s, self._start + e, out)
+        if hasattr(reader, "clone"):
+            self.parallel_readers = getattr(reader, "parallel_readers", 1)
+            self.clone = lambda: _SpanReader(reader.clone(), self._start, self._stop)
 
     def __len__(self) -> int:
         return self._stop - self._start

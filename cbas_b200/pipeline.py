@@ -140,10 +140,23 @@ class StreamedEncoder:
         once per chunk, after the chunk has been read (cbas.py:427-429)."""
         compute = torch.cuda.current_stream(self.enc.device)
         starts = list(range(0, video_len, self.chunk))
-        # one more staging slot than the pipeline depth: the reader fills slot k+1 while slots k, k-1 are in flight
-        while len(self.host_in) < self.depth + 1:
+        # Several decoders when the reader can provide them (`reader.clone()` / `reader.parallel_readers`): reader
+        # thread j owns chunks j, j+R, j+2R, ... and its own capture, so whole chunks decode side by side (OpenCV
+        # releases the GIL inside read / cvtColor) - the in-process counterpart of decode.ParallelVideoReader without
+        # the start-up cost of worker processes.  Staging slots: one per pipeline stage plus one per reader, rounded up
+        # to a multiple of R so that the chunks sharing a slot belong to the same thread (their order is then fixed).
+        R = max(1, min(int(getattr(reader, "parallel_readers", 1)), len(starts)))
+        readers = [reader]
+        try:
+            for _ in range(R - 1):
+                readers.append(reader.clone())
+        except Exception:
+            for r in readers[1:]:
+                r.close()
+            readers, R = [reader], 1
+        n_host = -(-(self.depth + R) // R) * R
+        while len(self.host_in) < n_host:
             self.host_in.append(torch.empty_like(self.host_in[0]).pin_memory())
-        n_host = len(self.host_in)
         ready = [threading.Event() for _ in starts]
         free = [threading.Event() for _ in range(n_host)]
         for f in free:
@@ -151,24 +164,26 @@ class StreamedEncoder:
         errors = []
         stop = threading.Event()
 
-        def read_loop():
+        def read_loop(j):
             try:
-                for k, s in enumerate(starts):
+                for k in range(j, len(starts), R):
+                    s = starts[k]
                     hs = k % n_host
                     while not free[hs].wait(0.05):
                         if stop.is_set():
                             return
                     free[hs].clear()
                     e = min(s + self.chunk, video_len)
-                    reader.read_into(s, e, self.host_in[hs][:e - s].numpy())
+                    readers[j].read_into(s, e, self.host_in[hs][:e - s].numpy())
                     ready[k].set()
             except BaseException as exc:  # re-raised in the calling thread
                 errors.append(exc)
                 for r in ready:
                     r.set()
 
-        th = threading.Thread(target=read_loop, name="cbas-b200-reader", daemon=True)
-        th.start()
+        threads = [threading.Thread(target=read_loop, args=(j,), name=f"cbas-b200-reader-{j}", daemon=True) for j in range(R)]
+        for th in threads:
+            th.start()
         pending = []  # (slot, n, host_slot)
         total = 0
 
@@ -201,5 +216,8 @@ class StreamedEncoder:
             raise
         finally:
             stop.set()
-            th.join(timeout=10)
+            for th in threads:
+                th.join(timeout=10)
+            for r in readers[1:]:
+                r.close()
         return total

@@ -374,3 +374,30 @@ def test_two_devices_in_one_process(tmp_path, monkeypatch):
         w.join(10)
     assert all(os.path.exists(c[:-4] + "_cls.h5") for c in clips)
     assert sum(w.tasks_processed_in_batch for w in workers) >= 0
+
+
+def test_encode_file_parallel_decode_threads_are_bit_identical(tmp_path, monkeypatch):
+    """mp4 -> `_cls.h5` with one in-process decoder (the reference's arrangement) and with four decoding whole chunks
+    side by side: the same embedding file, bit for bit, in both preprocessing modes."""
+    cv2 = pytest.importorskip("cv2")
+    p = str(tmp_path / "v.mp4")
+    vw = cv2.VideoWriter(p, cv2.VideoWriter_fourcc(*"mp4v"), 30.0, (64, 64))
+    if not vw.isOpened():
+        pytest.skip("no mp4 encoder in this OpenCV build")
+    base = np.random.default_rng(3).integers(0, 255, (64, 64, 3), dtype=np.uint8)
+    for i in range(230):
+        vw.write(np.roll(base, 3 * i, axis=1))
+    vw.release()
+    monkeypatch.setattr(gui_state, "proj", None)
+    monkeypatch.setattr(cbas, "CHUNK_SIZE", 32)
+    monkeypatch.setattr(cbas, "DECODE_WORKERS", 0)
+    for mode in ("reference", "processor"):
+        enc = DinoEncoder("synthetic:vits16@4", "cuda", preprocess=mode, image_size=64, max_frames=32)
+        outs = []
+        for threads in (1, 4):
+            monkeypatch.setattr(cbas, "DECODE_THREADS", threads)
+            out = cbas.encode_file(enc, p)
+            with store.EmbeddingReader(out) as r:
+                outs.append(r.read(0, r.shape[0]))
+            os.remove(out)
+        assert outs[0].shape == (230, 384) and np.array_equal(outs[0], outs[1]), mode

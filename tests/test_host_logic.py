@@ -159,6 +159,46 @@ def test_parallel_video_reader_matches_sequential_decode(tmp_path):
         ParallelVideoReader(str(tmp_path / "missing.mp4"))
 
 
+def test_cloned_readers_decode_whole_chunks_exactly(tmp_path):
+    """pipeline.run_reader gives each of several in-process decoders (VideoReader.clone) every R-th chunk: a clone that
+    seeks to its chunk and decodes it must produce the frames the single sequential reader produces, RGB and
+    green-plane form, and a frame-range view (one video on several GPUs) clones into the same range."""
+    cv2 = pytest.importorskip("cv2")
+    p = str(tmp_path / "v.mp4")
+    vw = cv2.VideoWriter(p, cv2.VideoWriter_fourcc(*"mp4v"), 30.0, (64, 48))
+    if not vw.isOpened():
+        pytest.skip("no mp4 encoder in this OpenCV build")
+    base = np.random.default_rng(1).integers(0, 255, (48, 64, 3), dtype=np.uint8)
+    for i in range(150):
+        vw.write(np.roll(base, 2 * i, axis=0))
+    vw.release()
+    seq = cbas.VideoReader(p)
+    want = seq.get_batch(range(0, len(seq)))
+    assert len(seq) == 150 and seq.parallel_readers >= 1
+    readers = [seq, seq.clone(), seq.clone()]
+    starts = list(range(0, 150, 32))
+    got = np.zeros_like(want)
+    green = np.zeros(want.shape[:3], np.uint8)
+    for j, r in enumerate(readers):          # reader j owns chunks j, j+3, ... like run_reader's threads
+        for k in range(j, len(starts), 3):
+            s, e = starts[k], min(starts[k] + 32, 150)
+            r.read_into(s, e, got[s:e])
+    for j, r in enumerate(reversed(readers)):  # and again with other owners, green plane only (REFERENCE mode)
+        for k in range(j, len(starts), 3):
+            s, e = starts[k], min(starts[k] + 32, 150)
+            r.read_into(s, e, green[s:e])
+    assert np.array_equal(got, want) and np.array_equal(green, want[..., 1])
+    span = cbas._SpanReader(seq, 40, 110)
+    twin = span.clone()
+    buf = np.zeros((30, 48, 64, 3), np.uint8)
+    twin.read_into(10, 40, buf)
+    assert len(twin) == 70 and np.array_equal(buf, want[50:80])
+    for r in readers[1:]:
+        r.close()
+    twin.close()
+    seq.close()
+
+
 def test_infer_file_swallows_errors_and_returns_none(tmp_path, capsys):
     out = cbas.infer_file(str(tmp_path / "nope_cls.h5"), nn.Linear(1, 1), "m", ["a"], 31, device="cpu")
     assert out is None and "Error during buffered inference" in capsys.readouterr().out
