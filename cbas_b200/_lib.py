@@ -112,6 +112,8 @@ SIGNATURES = {
     "cbas_b200_head_forward_windows": (C.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "cbas_b200_actogram_bins": (C.c_int, [c_void_p, c_int64, c_int32, c_int32, c_float, c_int64, c_void_p,
                                           c_void_p]),
+    "cbas_b200_actogram_bins_f64": (C.c_int, [c_void_p, c_int64, c_int32, c_int32, C.c_double, c_int64, c_void_p,
+                                              c_void_p]),
 }
 
 

@@ -457,7 +457,7 @@ class Actogram:
         events_parts = []
         for df in tables:
             cols = list(df.columns)
-            probs = np.ascontiguousarray(df.to_numpy(dtype=np.float32))
+            probs = np.ascontiguousarray(df.to_numpy(dtype=np.float64))  # compared in float64, like the reference
             events_parts.append((probs, cols.index(self.behavior)))
         self.binned_activity = [float(v) for v in _bin_tables(events_parts, self.threshold, self.binsize_frames)]
 

@@ -276,17 +276,17 @@ def synthetic_head_state_dict(in_features: int = 768, out_features: int = 9, bot
 
 
 def actogram_bins(probs: torch.Tensor, behavior: int, threshold: float, bin_frames: int) -> torch.Tensor:
-    """Numeric core of Actogram.__init__ (cbas.py:969-999) on the GPU: probs float32 [N,C] (CUDA) -> int32 bin
-    counts [ceil(N / bin_frames)]."""
-    if probs.dtype != torch.float32 or probs.dim() != 2 or not probs.is_cuda:
-        raise ValueError("actogram_bins expects a float32 [N,C] CUDA tensor")
+    """Numeric core of Actogram.__init__ (cbas.py:969-999) on the GPU: probs [N,C] (CUDA; float32 for probabilities
+    that stayed on the device, float64 for tables parsed from CSV files, compared in float64 like the reference) ->
+    int32 bin counts [ceil(N / bin_frames)]."""
+    if probs.dtype not in (torch.float32, torch.float64) or probs.dim() != 2 or not probs.is_cuda:
+        raise ValueError("actogram_bins expects a float32 or float64 [N,C] CUDA tensor")
     probs = probs.contiguous()
     n, c = probs.shape
     nb = (n + bin_frames - 1) // bin_frames if bin_frames > 0 else 0
     bins = torch.zeros(nb, device=probs.device, dtype=torch.int32)
     if n and nb:
-        _lib.check(_lib.lib().cbas_b200_actogram_bins(probs.data_ptr(), n, c, int(behavior), float(threshold),
-                                                      int(bin_frames), bins.data_ptr(),
-                                                      torch.cuda.current_stream(probs.device).cuda_stream),
-                   "actogram_bins")
+        fn = _lib.lib().cbas_b200_actogram_bins if probs.dtype == torch.float32 else _lib.lib().cbas_b200_actogram_bins_f64
+        _lib.check(fn(probs.data_ptr(), n, c, int(behavior), float(threshold), int(bin_frames), bins.data_ptr(),
+                      torch.cuda.current_stream(probs.device).cuda_stream), "actogram_bins")
     return bins

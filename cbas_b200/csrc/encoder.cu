@@ -363,6 +363,19 @@ int encoder_embed(cbas_encoder* e, const uint8_t* frames_u8, int pix, const floa
         count_launch();
         if (int rc = check_cuda(cudaGetLastError(), "add_pos_embed_kernel launch")) return rc;
     }
+    if (!e->ln_fused) {
+        // standalone LayerNorm kernels read h themselves: only the CLS / register rows are left to write
+        // (HF modeling_dinov3_vit.py:85-90: cat(cls, registers, patches))
+        ProfScope prof(PROF_PATCH_GEMM, s);
+        const long long total = (long long)n * c.prefix_tokens * (D / 4);
+        if (total > 0) {
+            fill_prefix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(e->h, (const float*)e->w.prefix, n, e->T,
+                                                                              c.prefix_tokens, D);
+            count_launch();
+            if (int rc = check_cuda(cudaGetLastError(), "fill_prefix_kernel launch")) return rc;
+        }
+        return 0;
+    }
     // CLS / register rows into h, then the row statistics and the shifted bf16 copy that block 0's QKV GEMM reads
     return launch_ln_stats_init(e->h, (const float*)e->w.prefix, e->T, c.prefix_tokens, e->hb, e->stats[0], n * e->T, D, s);
 }

@@ -499,28 +499,29 @@ head_pool_kernel(const PoolParams p) {
 
 // ---------------------------------------------------------------------------------------------- actogram
 // bins[k] = #{ f in bin k : p_b(f) * [max_{b'!=b} p_b'(f) < p_b(f)] >= threshold }   (cbas.py:989-999)
+// Real = float for probabilities that never left the GPU, double for tables parsed from the CSV files (the reference
+// compares the float64 values pandas parsed against a float64 threshold, cbas.py:991-993).
+template <typename Real>
 __global__ void __launch_bounds__(256)
-actogram_bins_kernel(const float* __restrict__ probs, long long n, int C, int behavior, float thr, long long bin_frames,
+actogram_bins_kernel(const Real* __restrict__ probs, long long n, int C, int behavior, Real thr, long long bin_frames,
                      int* __restrict__ bins) {
     const long long bin = blockIdx.x;
     const long long f0 = bin * bin_frames;
     const long long f1 = f0 + bin_frames < n ? f0 + bin_frames : n;
     int count = 0;
     for (long long f = f0 + threadIdx.x; f < f1; f += blockDim.x) {
-        const float* r = probs + f * C;
-        const float pb = r[behavior];
-        float others = -INFINITY;
-        bool any = false, nan_other = false;
+        const Real* r = probs + f * C;
+        const Real pb = r[behavior];
+        Real others = -INFINITY;
+        bool any = false;
         for (int c = 0; c < C; ++c)
             if (c != behavior) {
                 any = true;
-                nan_other |= isnan(r[c]);
-                others = fmaxf(others, r[c]);
+                others = fmax(others, r[c]);  // like pandas max(axis=1), fmax skips NaN
             }
-        // pandas max(axis=1) skips NaN; with no other column it is NaN and `NaN < p` is False
-        (void)nan_other;
+        // with no other column the row maximum is NaN and `NaN < p` is False
         const bool is_max = any && (others < pb);
-        const float v = is_max ? pb : pb * 0.0f;
+        const Real v = is_max ? pb : pb * Real(0);
         count += (v >= thr) ? 1 : 0;
     }
     __shared__ int sh[8];
@@ -533,6 +534,29 @@ actogram_bins_kernel(const float* __restrict__ probs, long long n, int C, int be
         bins[bin] = tot;
     }
 }
+
+template <typename Real>
+static int actogram_bins_impl(const Real* probs_dev, int64_t n, int32_t C, int32_t behavior, Real threshold,
+                              int64_t bin_frames, int32_t* bins_out_dev, void* stream) {
+    if (n < 0 || C < 1 || behavior < 0 || behavior >= C) return fail("actogram: bad shape or behaviour index");
+    if (bin_frames <= 0) return fail("actogram: bin size must be positive");
+    if (n == 0) return 0;
+    if (!probs_dev || !bins_out_dev) return fail("null argument");
+    const long long nb = (n + bin_frames - 1) / bin_frames;
+    if (nb > 0x7fffffffLL) return fail("actogram: too many bins");
+    // no handle here: run on the device that owns the input, whatever the calling thread's current device is
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, probs_dev) != cudaSuccess || attr.type != cudaMemoryTypeDevice)
+        return fail("actogram: probs_dev is not device memory");
+    DeviceGuard guard(attr.device);
+    if (!guard.ok()) return fail("cudaSetDevice to the input's device failed");
+    ProfScope prof(PROF_ACTOGRAM, (cudaStream_t)stream);
+    actogram_bins_kernel<Real><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(probs_dev, n, C, behavior, threshold,
+                                                                              bin_frames, bins_out_dev);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "actogram_bins_kernel launch");
+}
+
 
 // host-side helpers ------------------------------------------------------------------------------
 uint16_t f2bf(float f) {
@@ -889,23 +913,12 @@ int cbas_b200_head_forward_windows(cbas_head* h, const float* x_f32_dev, int64_t
 
 int cbas_b200_actogram_bins(const float* probs_dev, int64_t n, int32_t C, int32_t behavior, float threshold,
                             int64_t bin_frames, int32_t* bins_out_dev, void* stream) {
-    if (n < 0 || C < 1 || behavior < 0 || behavior >= C) return fail("actogram: bad shape or behaviour index");
-    if (bin_frames <= 0) return fail("actogram: bin size must be positive");
-    if (n == 0) return 0;
-    if (!probs_dev || !bins_out_dev) return fail("null argument");
-    const long long nb = (n + bin_frames - 1) / bin_frames;
-    if (nb > 0x7fffffffLL) return fail("actogram: too many bins");
-    // no handle here: run on the device that owns the input, whatever the calling thread's current device is
-    cudaPointerAttributes attr{};
-    if (cudaPointerGetAttributes(&attr, probs_dev) != cudaSuccess || attr.type != cudaMemoryTypeDevice)
-        return fail("actogram: probs_dev is not device memory");
-    DeviceGuard guard(attr.device);
-    if (!guard.ok()) return fail("cudaSetDevice to the input's device failed");
-    ProfScope prof(PROF_ACTOGRAM, (cudaStream_t)stream);
-    actogram_bins_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(probs_dev, n, C, behavior, threshold,
-                                                                        bin_frames, bins_out_dev);
-    count_launch();
-    return check_cuda(cudaGetLastError(), "actogram_bins_kernel launch");
+    return actogram_bins_impl<float>(probs_dev, n, C, behavior, threshold, bin_frames, bins_out_dev, stream);
+}
+
+int cbas_b200_actogram_bins_f64(const double* probs_dev, int64_t n, int32_t C, int32_t behavior, double threshold,
+                                int64_t bin_frames, int32_t* bins_out_dev, void* stream) {
+    return actogram_bins_impl<double>(probs_dev, n, C, behavior, threshold, bin_frames, bins_out_dev, stream);
 }
 
 }  // extern "C"

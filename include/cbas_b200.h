@@ -234,6 +234,11 @@ int cbas_b200_head_forward_windows(cbas_head* head, const float* x_f32_dev, int6
  * (last partial bin kept).  probs_dev f32 [n, C]; bins_out_dev int32 [ceil(n / bin_frames)]. */
 int cbas_b200_actogram_bins(const float* probs_dev, int64_t n, int32_t C, int32_t behavior, float threshold,
                             int64_t bin_frames, int32_t* bins_out_dev, void* stream);
+/* The same over float64 probabilities and a float64 threshold: what Actogram.__init__ computes on the tables pandas
+ * parsed from the `_outputs.csv` files (cbas.py:989-993), so that a probability that rounds across the threshold in
+ * float32 is counted as the reference counts it. */
+int cbas_b200_actogram_bins_f64(const double* probs_dev, int64_t n, int32_t C, int32_t behavior, double threshold,
+                                int64_t bin_frames, int32_t* bins_out_dev, void* stream);
 
 #ifdef __cplusplus
 }

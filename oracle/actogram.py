@@ -22,7 +22,8 @@ def actogram_bins(probs: np.ndarray, behavior: int, threshold: float, bin_frames
         return np.zeros(0, np.int64)
     p = probs[:, behavior]
     if c > 1:
-        others = np.delete(probs, behavior, axis=1).max(axis=1)
+        # DataFrame.max(axis=1) skips NaN cells (skipna=True); a row of nothing but NaN stays NaN and `NaN < p` is False
+        others = np.fmax.reduce(np.delete(probs, behavior, axis=1), axis=1)
         is_max = others < p
     else:
         is_max = np.zeros(n, bool)

@@ -178,3 +178,24 @@ def test_actogram_vs_oracle_large_and_edges():
     for thr in (0.5, 0.0):  # 0 >= 0.5 never; 0 >= 0.0 always (what pandas/numpy give in the reference)
         np.testing.assert_array_equal(actogram_bins(one, 0, thr, 10).cpu().numpy(),
                                       oact.actogram_bins(one.cpu().numpy(), 0, thr, 10))
+
+
+def test_actogram_float64_tables_compare_like_the_reference():
+    """Actogram reads the `_outputs.csv` tables as float64 and compares in float64 (cbas.py:989-993): a probability
+    just under the threshold that float32 would round up onto it must not count, ties of the other-behaviour maximum
+    are decided on the float64 values, NaN cells are skipped by the row maximum."""
+    thr = 0.7
+    below = np.nextafter(np.float64(np.float32(thr)), 0.0)        # float32(thr) rounds ABOVE 0.7; one float64 step below it
+    rows = np.array([[0.1, np.float64(np.float32(thr)), 0.2],     # >= 0.7 in float64: counts
+                     [0.1, 0.7 - 1e-12, 0.2],                     # float32 rounds it to float32(0.7) >= thr32: must NOT count
+                     [0.1, below, 0.2],
+                     [0.8, 0.8 + 1e-13, 0.0],                     # is_max decided in float64 (float32 sees a tie): counts
+                     [np.nan, 0.9, 0.3],                          # NaN skipped by max(axis=1): counts
+                     [0.95, 0.9, 0.0]], dtype=np.float64)
+    want = oact.actogram_bins(rows, 1, thr, 2)
+    got = actogram_bins(torch.from_numpy(rows).cuda(), 1, thr, 2).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    assert want.tolist() == [0, 1, 1]
+    # the same table through float32 WOULD count row 1 (the rounding the float64 path exists to avoid)
+    got32 = actogram_bins(torch.from_numpy(rows.astype(np.float32)).cuda(), 1, thr, 2).cpu().numpy()
+    assert got32.tolist() != want.tolist()

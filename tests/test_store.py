@@ -90,3 +90,35 @@ def test_corrupt_and_foreign_files(tmp_path):
     w.close()
     with pytest.raises(KeyError):
         store.EmbeddingReader(str(tmp_path / "t.h5"), backend="native")
+
+
+def test_interop_with_h5py_both_directions(tmp_path):
+    """Runs only where h5py (the reference's own HDF5 library) is importable - it is in neither development image: a
+    file from the native writer opened by libhdf5 (shape, dtype, chunking, unlimited first axis, string attributes,
+    data), and a file h5py wrote read by the native reader and through store.EmbeddingReader."""
+    h5py = pytest.importorskip("h5py")
+    rng = np.random.default_rng(0)
+    emb = rng.standard_normal((9000, 768)).astype(np.float32)
+    attrs = {"encoder_model_identifier": "facebook/dinov3-vitb16-pretrain-lvd1689m", "schema_version": "1.0"}
+    p = str(tmp_path / "native_cls.h5")
+    w = store.EmbeddingWriter(p, 768, attrs, backend="native")
+    for i in range(0, 9000, 512):
+        w.append(emb[i:i + 512])
+        w.flush()
+    w.close()
+    with h5py.File(p, "r") as f:
+        d = f["cls"]
+        assert d.shape == (9000, 768) and d.dtype == np.float16 and d.maxshape == (None, 768)
+        assert d.chunks == (store.CHUNK_ROWS, 768)
+        assert {k: (v.decode() if isinstance(v, bytes) else str(v)) for k, v in f.attrs.items()} == attrs
+        np.testing.assert_array_equal(d[...], emb.astype(np.float16))
+        np.testing.assert_array_equal(d[4000:4100], emb[4000:4100].astype(np.float16))
+    q = str(tmp_path / "h5py_cls.h5")
+    w = store.EmbeddingWriter(q, 768, attrs, backend="h5py")
+    w.append(emb)
+    w.close()
+    with hdf5_min.File(q) as f:
+        assert f["cls"].shape == (9000, 768)
+        np.testing.assert_array_equal(f["cls"][100:700], emb[100:700].astype(np.float16))
+    with store.EmbeddingReader(q) as r:
+        assert r.shape == (9000, 768) and r.attrs == attrs
