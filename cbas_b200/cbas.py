@@ -73,12 +73,18 @@ class VideoReader:
         self._arr = None
         self._decord = None
         self._pos = 0
+        self._fd = None
         if path.lower().endswith(".npy"):
             self._arr = np.load(path, mmap_mode="r")
             if self._arr.ndim != 4 or self._arr.shape[-1] != 3 or self._arr.dtype != np.uint8:
                 raise ValueError(f"{path}: expected a uint8 [N,H,W,3] array")
             self._len = int(self._arr.shape[0])
             self.frame_hw = (int(self._arr.shape[1]), int(self._arr.shape[2]))
+            # whole frames are read with pread() straight into the caller's (pinned) buffer: the kernel copies out of
+            # the page cache without the per-page faults a fresh memory map costs (one per 4 KB, every call)
+            if self._arr.flags["C_CONTIGUOUS"] and hasattr(os, "preadv"):
+                self._fd = os.open(path, os.O_RDONLY)
+                self._data_offset = int(self._arr.offset)
             return
         try:
             import decord  # type: ignore
@@ -121,7 +127,7 @@ class VideoReader:
         if not cap.isOpened():
             raise RuntimeError(f"could not open video '{self.path}'")
         other = VideoReader.__new__(VideoReader)
-        other.path, other._cap, other._arr, other._decord, other._pos = self.path, cap, None, None, 0
+        other.path, other._cap, other._arr, other._decord, other._pos, other._fd = self.path, cap, None, None, 0, None
         other._len, other.frame_hw = self._len, self.frame_hw
         return other
 
@@ -152,6 +158,26 @@ class VideoReader:
             return
         green = out.ndim == 3  # [n,H,W]: the caller wants the green plane only
         if self._arr is not None:
+            if not green and self._fd is not None and out.flags["C_CONTIGUOUS"]:
+                frame_bytes = int(np.prod(self._arr.shape[1:]))
+                dst = memoryview(out).cast("B")
+                parts = min(_COPY_THREADS, n)
+                cuts = [n * i // parts for i in range(parts + 1)]
+
+                def pread_part(ab):
+                    lo, hi = ab[0] * frame_bytes, ab[1] * frame_bytes
+                    off = self._data_offset + start * frame_bytes
+                    while lo < hi:  # pread may return short counts
+                        got = os.preadv(self._fd, [dst[lo:hi]], off + lo)
+                        if got <= 0:
+                            raise IOError(f"short read from '{self.path}'")
+                        lo += got
+
+                if parts <= 1:
+                    pread_part((0, n))
+                else:
+                    list(_copy_pool().map(pread_part, zip(cuts[:-1], cuts[1:])))
+                return
             src = self._arr[start:stop, :, :, 1] if green else self._arr[start:stop]
             parts = min(_COPY_THREADS, n)
             if parts <= 1:
@@ -182,6 +208,9 @@ class VideoReader:
     def close(self):
         if self._cap is not None:
             self._cap.release()
+        if getattr(self, "_fd", None) is not None:
+            os.close(self._fd)
+            self._fd = None
 
 
 class _SpanReader:
