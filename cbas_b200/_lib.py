@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CBAS_B200_LIB") or os.path.join(_HERE, "libcbas_b200.so")
 
 ABI_VERSION = 3  # CBAS_B200_ABI_VERSION in include/cbas_b200.h
-OPT_ATTENTION_IMPL, OPT_PRUNE_LAST_LAYER, OPT_RESIZE_KERNEL, OPT_LN_FUSION = 0, 1, 2, 3  # cbas_b200_encoder_set_option
+OPT_ATTENTION_IMPL, OPT_PRUNE_LAST_LAYER, OPT_RESIZE_KERNEL, OPT_LN_FUSION, OPT_SERPENTINE = 0, 1, 2, 3, 4  # cbas_b200_encoder_set_option
 
 _lib = None
 _lock = threading.Lock()

@@ -58,6 +58,7 @@ struct AttnTcParams {
     const float* rope_sin;
     int prefix;
     long long* trace;          // optional [64][ATC_TRACE_SLOTS] clock64 stamps of CTA 0 (profiling aid; null in production)
+    int reverse;               // walk the frames from the last to the first (attention_tc_kernel only; see GemmParams::reverse)
 };
 
 __host__ __device__ inline int atc_set_bytes(int TK) { return 2 * 128 * 128 + 2 * TK * 128; }
@@ -396,7 +397,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
         int it = 0;
         for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
             const int b = it & 1;
-            const int f = w / p.heads, h = w % p.heads;
+            const int f = p.reverse ? p.frames - 1 - w / p.heads : w / p.heads, h = w % p.heads;
             uint8_t* set = smem + b * set_bytes;
             const int row0 = f * T;
             mbar_wait(&qk_empty[b], ((it >> 1) & 1) ^ 1);
@@ -503,7 +504,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
         const int sbase = 6 + 5 * mt;
         int it = 0;
         for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
-            const int f = w / p.heads, h = w % p.heads;
+            const int f = p.reverse ? p.frames - 1 - w / p.heads : w / p.heads, h = w % p.heads;
             // The two query tiles take turns in the softmax: tile 1 starts item i only when tile 0 has handed over its
             // P of item i, tile 0 starts item i+1 when tile 1 has handed over item i.  One tile's S / P V MMAs, TMEM drain
             // and stores then always fall into the other tile's exponentials instead of both tiles queueing for the

@@ -76,6 +76,8 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
 // Row-major [rows, cols] tensor map, box box_cols x box_rows with a 128-byte inner extent, SWIZZLE_128B.
 int make_tmap_2d(CUtensorMap* map, const void* base, bool f32, int rows, int cols, int ld, int box_cols, int box_rows);
 int make_tmap_3d_bf16(CUtensorMap* map, const void* base, int d0, int d1, int d2, int ld, int box0, int box1);
+int make_tmap_3d_f32(CUtensorMap* map, const void* base, long long d0, long long d1, long long d2, long long pitch1,
+                     long long pitch2, int box0, int box1, int box2);
 void set_gemm_cta_group(int cg);  // 0 auto, 1 single-CTA tiles, 2 CTA-pair tiles
 
 #define CBAS_CHECK(expr)                                   \

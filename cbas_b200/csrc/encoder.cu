@@ -49,6 +49,10 @@ preprocess_plane_kernel(const float* __restrict__ planes, __nv_bfloat16* __restr
     reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
+// Direction of the next row-streaming launch of this host thread (encoder_layer_unfused alternates it kernel by
+// kernel when the handle's serpentine option is on; 0 everywhere else).
+thread_local int t_reverse = 0;
+
 template <typename OutT>
 int launch_layernorm(const float* in, long long in_row_stride, const float* g, const float* b, OutT* out, int rows,
                      int D, float eps, cudaStream_t s, int tag = PROF_LAYERNORM) {
@@ -57,11 +61,11 @@ int launch_layernorm(const float* in, long long in_row_stride, const float* g, c
     const int threads = 256, rows_per_block = threads / 32;
     const int grid = (rows + rows_per_block - 1) / rows_per_block;
     switch (D) {
-        case 384: layernorm_kernel<384, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps); break;
-        case 768: layernorm_kernel<768, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps); break;
-        case 1024: layernorm_kernel<1024, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps); break;
-        case 128: layernorm_kernel<128, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps); break;
-        case 256: layernorm_kernel<256, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps); break;
+        case 384: layernorm_kernel<384, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps, t_reverse); break;
+        case 768: layernorm_kernel<768, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps, t_reverse); break;
+        case 1024: layernorm_kernel<1024, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps, t_reverse); break;
+        case 128: layernorm_kernel<128, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps, t_reverse); break;
+        case 256: layernorm_kernel<256, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps, t_reverse); break;
         default: return fail("LayerNorm width " + std::to_string(D) + " not instantiated (384/768/1024)");
     }
     count_launch();
@@ -195,7 +199,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, const floa
     const int smem = atc_smem_bytes(TK, T, prefix, rope);
     if (smem > 232448) return fail("attention: frame does not fit in shared memory");
     AttnTcParams p{qkv, out, frames, heads, T, TK, D, 0.125f * 1.4426950408889634f, rope ? cs : nullptr,
-                   rope ? sn : nullptr, prefix, g_attention_trace};
+                   rope ? sn : nullptr, prefix, g_attention_trace, t_reverse};
     const int items = frames * heads;
     const int grid = items < sm_count() ? items : sm_count();
     switch (TK) {  // the padded key count is a template parameter: every softmax / MMA loop is fully unrolled
@@ -273,6 +277,8 @@ struct cbas_encoder {
     int attention_impl = 0;            // 0 auto, 1 mma.sync, 2 tcgen05
     int resize_tiled = 2;              // 0 per-pixel kernel, 1 general tiled kernel, 2 column-per-thread kernel
     int ln_fused = CBAS_LN_FUSED_DEFAULT;  // 1: norm1 / norm2 inside the GEMM epilogues, 0: standalone LayerNorm kernels
+    bool serpentine = true;            // standalone-LayerNorm path: consecutive kernels walk the rows in opposite directions
+    int direction = 0;                 //   ... direction of the last kernel launched by the previous block
     float* ones = nullptr;             // [D] ones / zeros: unit gamma and zero beta for the standalone LayerNorm path
     float* zeros = nullptr;            //     (gamma and beta themselves are folded into the weights either way)
     // workspace (device)
@@ -408,6 +414,16 @@ int encoder_layer_unfused(cbas_encoder* e, int li, int n, cudaStream_t s, bool c
     const cbas_layer_weights& L = e->layers[li];
     const int D = c.hidden, I = c.intermediate, T = e->T, M = n * T;
     const bool tc = use_attention_tc(e->attention_impl, T, c.prefix_tokens, e->w.rope_cos != nullptr);
+    // Serpentine order: every kernel of the block walks the rows (frames) in the direction opposite to its
+    // predecessor's, so it starts on the ~100 MB its predecessor touched last and finds them in the 126 MB L2
+    // instead of HBM.  The direction carries over from block to block (seven kernels per block: it alternates).
+    struct Direction {
+        bool on;
+        ~Direction() { t_reverse = 0; }
+        void flip() const { if (on) t_reverse ^= 1; }
+    } dir{e->serpentine && !cls_only};
+    t_reverse = dir.on ? e->direction : 0;
+    dir.flip();
     if (int rc = launch_layernorm<__nv_bfloat16>(e->h, 1, e->ones, e->zeros, e->hb, M, D, c.ln_eps, s)) return rc;
     const __nv_bfloat16* wqkv = (const __nv_bfloat16*)L.w_qkv;
     const float* bqkv = (const float*)L.b_qkv;
@@ -416,7 +432,9 @@ int encoder_layer_unfused(cbas_encoder* e, int li, int n, cudaStream_t s, bool c
         // V is stored as f16 for the tcgen05 kernels; the T <= 256 kernel takes q and k as f16 as well
         p.M = M; p.N = 3 * D; p.K = D; p.bias = bqkv; p.out = e->qkv; p.ldo = 3 * D;
         p.f16_from = attention_qk_f16(T) ? 0 : 2 * D;
+        dir.flip(); p.reverse = t_reverse;
         if (int rc = launch_gemm(e->hb, D, wqkv, D, p, tc ? EPI_BIAS_BF16_VF16 : EPI_BIAS_BF16, s, PROF_QKV_GEMM)) return rc;
+        dir.flip();
         if (tc) {
             if (int rc = launch_attention_tc(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n, T,
                                              c.prefix_tokens, c.heads, s)) return rc;
@@ -424,13 +442,18 @@ int encoder_layer_unfused(cbas_encoder* e, int li, int n, cudaStream_t s, bool c
                                              c.prefix_tokens, c.heads, s)) return rc;
         p = GemmParams{};
         p.M = M; p.N = D; p.K = D; p.bias = (const float*)L.b_o; p.out = e->h; p.ldo = D;
+        dir.flip(); p.reverse = t_reverse;
         if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_o, D, p, EPI_RESID_F32, s, PROF_PROJ_GEMM)) return rc;
+        dir.flip();
         if (int rc = launch_layernorm<__nv_bfloat16>(e->h, 1, e->ones, e->zeros, e->hb, M, D, c.ln_eps, s)) return rc;
         p = GemmParams{};
         p.M = M; p.N = I; p.K = D; p.bias = (const float*)L.b_up; p.out = e->u; p.ldo = I;
+        dir.flip(); p.reverse = t_reverse;
         if (int rc = launch_gemm(e->hb, D, (const __nv_bfloat16*)L.w_up, D, p, EPI_BIAS_GELU_BF16, s, PROF_UP_GEMM)) return rc;
         p = GemmParams{};
         p.M = M; p.N = D; p.K = I; p.bias = (const float*)L.b_down; p.out = e->h; p.ldo = D;
+        dir.flip(); p.reverse = t_reverse;
+        e->direction = t_reverse;
         return launch_gemm(e->u, I, (const __nv_bfloat16*)L.w_down, I, p, EPI_RESID_F32, s, PROF_DOWN_GEMM);
     }
     // last block, CLS rows only (see encoder_last_layer_cls_only)
@@ -682,6 +705,7 @@ int cbas_b200_encoder_set_option(cbas_encoder* enc, int32_t option, int32_t valu
         case CBAS_OPT_PRUNE_LAST_LAYER: enc->prune_last_layer = value != 0; return 0;
         case CBAS_OPT_RESIZE_KERNEL: enc->resize_tiled = value < 0 ? 0 : (value > 2 ? 2 : value); return 0;
         case CBAS_OPT_LN_FUSION: enc->ln_fused = value != 0; return 0;
+        case CBAS_OPT_SERPENTINE: enc->serpentine = value != 0; return 0;
     }
     return fail("unknown encoder option " + std::to_string(option));
 }

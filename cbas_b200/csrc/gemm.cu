@@ -161,4 +161,22 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, int d0, int d1, int d2
     return 0;
 }
 
+
+// fp32 [d2][d1][d0] tensor (d0 contiguous, pitches in BYTES), box box0 x box1 x box2 with a 128-byte inner extent
+// (box0 = 32 floats), SWIZZLE_128B; out-of-range elements read as zero
+int make_tmap_3d_f32(CUtensorMap* map, const void* base, long long d0, long long d1, long long d2, long long pitch1,
+                     long long pitch2, int box0, int box1, int box2) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch1, (cuuint64_t)pitch2};
+    cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, (cuuint32_t)box2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (3-D fp32) failed with CUresult " + std::to_string((int)r));
+    return 0;
+}
+
 }  // namespace cbas

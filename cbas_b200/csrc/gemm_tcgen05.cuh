@@ -91,6 +91,9 @@ struct GemmParams {
     float ln_eps;
     void* hb;
     int ldhb;
+    // walk the row blocks from the last to the first (encoder.cu: consecutive kernels alternate direction, so each one
+    // starts on the rows its predecessor touched last, which are still in L2).  Not supported by the LN producers.
+    int reverse;
 };
 
 constexpr int GEMM_BLOCK_M = 128;
@@ -214,7 +217,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ---------------------------------------------------------------- TMA producer (whole warp, one elected lane)
         uint32_t stage = 0, phase = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-            const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+            const int m_blk = p.reverse ? m_blocks - 1 - tile / n_blocks : tile / n_blocks, n_blk = tile % n_blocks;
             const int a_row = (m_blk * CG + (int)cta_rank) * GEMM_BLOCK_M;
             const int b_row = n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / CG);
             for (int kb = 0; kb < k_blocks; ++kb) {
@@ -282,7 +285,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (p.ln_in) {
                 int iter = 0;
                 for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++iter) {
-                    const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+                    const int m_blk = p.reverse ? m_blocks - 1 - tile / n_blocks : tile / n_blocks, n_blk = tile % n_blocks;
                     const int m_base = (m_blk * CG + (int)cta_rank) * GEMM_BLOCK_M;
                     // this tile's per-column constants (BLOCK_N floats each): first touch by this warp, L1 hits for the
                     // epilogue warps
@@ -354,7 +357,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             int iter = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++iter) {
-                const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+                const int m_blk = p.reverse ? m_blocks - 1 - tile / n_blocks : tile / n_blocks, n_blk = tile % n_blocks;
                 const int m_base = (m_blk * CG + (int)cta_rank) * GEMM_BLOCK_M;
                 const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
                 const int row = m_base + row_in_tile;
@@ -456,7 +459,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t sbuf = 0;  // which of the group's two staging slabs the next slab uses
         int iter = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++iter) {
-            const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+            const int m_blk = p.reverse ? m_blocks - 1 - tile / n_blocks : tile / n_blocks, n_blk = tile % n_blocks;
             const int m_base = (m_blk * CG + (int)cta_rank) * GEMM_BLOCK_M;  // first output row of this CTA
             const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
             // fused LayerNorm, consumer side: this row's rstd and -mean * rstd, prepared by the helper warp

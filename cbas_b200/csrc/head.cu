@@ -14,10 +14,11 @@
 //   H4 tcgen05 GEMM       Z = GELU(a W0^T + b0)                      [rows, 256] fp32
 //   H5 head_center_split  z - mean_t z  -> bf16 hi/lo
 //   H6 tcgen05 GEMM       G = z (Wih_f | Wih_r)^T + (b_ih + b_hh)    [rows, 512] fp32  (input half of the gates)
-//   H7 head_lstm_dir      the recurrence: W_hh of one direction resident in shared memory (fp32, 64 KB; for
-//                         lstm_hidden_size 128 the 256 KB matrix is streamed through L1/L2 instead), each
-//                         warp advances 4 windows at a time (register-tiled, h broadcast from shared memory),
-//                         only the steps that can reach the centre frames are run (21 of 31 per direction).
+//   H7 head_lstm_tc       the recurrence (lstm_hidden_size 64): persistent tcgen05 kernel, 128 windows per CTA, W_hh
+//                         (bf16 hi / lo) resident in shared memory, h fed back through shared memory, c in registers,
+//                         gates in TMEM (head_lstm_tc.cuh); only the steps that can reach the centre frames are run
+//                         (21 of 31 per direction).  lstm_hidden_size 128: head_lstm_dir, fp32 FMA, 4 windows per
+//                         warp, the 256 KB W_hh streamed through L1/L2.
 //                         lstm_layers = 2: layer 0 runs all steps, its [fwd|rev] outputs are split to bf16 hi/lo
 //                         and go through one more input-gate GEMM (H6') and recurrence (H7').
 //   use_acceleration = False is the same pipeline with a zero acceleration stream (zero bottleneck / LayerNorm
@@ -32,6 +33,7 @@
 #include "../../include/cbas_b200.h"
 #include "common.h"
 #include "gemm_tcgen05.cuh"
+#include "head_lstm_tc.cuh"
 
 #include <cmath>
 #include <cstring>
@@ -613,12 +615,16 @@ struct cbas_head {
     __nv_bfloat16* wih[2] = {nullptr, nullptr};
     float* bg[2] = {nullptr, nullptr};
     float* whh_t[2] = {nullptr, nullptr};
+    // lstm_hidden 64 (tcgen05 recurrence): the gate columns of wih / bg are ordered 4 * unit + gate inside a direction
+    // and the recurrent weights are [2 dir][hi, lo][256 columns][64 k] bf16 (head_lstm_tc.cuh)
+    __nv_bfloat16* whh_tc[2] = {nullptr, nullptr};
     float *b3 = nullptr, *ln_g = nullptr, *ln_b = nullptr, *b0 = nullptr;
     float *lin1_w = nullptr, *lin1_b = nullptr, *lin2_w = nullptr, *lin2_b = nullptr, *att_w = nullptr;
     float att_b = 0.f, inv_att_temp = 1.f, gate_sig = 0.5f;
     // workspace
     long long cap_frames = 0;
-    int chunk_windows = 4096;
+    int max_chunk_windows = 2 * 148 * 128;  // windows per pass of the window stages: two waves of 128-window tiles
+    int chunk_windows = 0;                  // ... the chunk workspace currently holds (grown on demand)
     __nv_bfloat16* xs = nullptr;  // [cap, 3F]
     float* P = nullptr;           // [cap, 384]
     float* q = nullptr;           // [cap, C]
@@ -643,6 +649,23 @@ int head_ensure_ws(cbas_head* h, long long n) {
     CBAS_CHECK(cudaMalloc((void**)&h->P, (size_t)n * 384 * 4));
     CBAS_CHECK(cudaMalloc((void**)&h->q, (size_t)n * C * 4));
     h->cap_frames = n;
+    return 0;
+}
+// workspace of the per-window stages for chunks of up to `windows` windows (grows, never shrinks)
+int head_ensure_chunk_ws(cbas_head* h, int windows) {
+    if (windows <= h->chunk_windows) return 0;
+    cudaFree(h->A); cudaFree(h->Z); cudaFree(h->G); cudaFree(h->H0); cudaFree(h->H); cudaFree(h->lin);
+    h->A = nullptr; h->Z = nullptr; h->G = nullptr; h->H0 = nullptr; h->H = nullptr; h->lin = nullptr;
+    h->chunk_windows = 0;
+    const int T = h->cfg.seq_len, HS = h->cfg.lstm_hidden, C = h->cfg.out_features;
+    const size_t rows = (size_t)windows * T;
+    CBAS_CHECK(cudaMalloc((void**)&h->A, rows * 1152 * 2));
+    CBAS_CHECK(cudaMalloc((void**)&h->Z, rows * HEAD_LIN0 * 4));
+    CBAS_CHECK(cudaMalloc((void**)&h->G, rows * 8 * HS * 4));
+    if (h->cfg.lstm_layers == 2) CBAS_CHECK(cudaMalloc((void**)&h->H0, rows * 2 * HS * 4));
+    CBAS_CHECK(cudaMalloc((void**)&h->H, (size_t)windows * (h->r - h->l) * 2 * HS * 4));
+    CBAS_CHECK(cudaMalloc((void**)&h->lin, (size_t)windows * C * 4));
+    h->chunk_windows = windows;
     return 0;
 }
 }  // namespace
@@ -712,9 +735,16 @@ int cbas_b200_head_create(const cbas_head_cfg* cfg, const cbas_head_weights* w, 
         std::vector<float> wf, wr, bif, bhf, bir, bhr;
         if (!rc) rc = download(wif, (size_t)4 * HS * Kin, wf);
         if (!rc) rc = download(wir, (size_t)4 * HS * Kin, wr);
+        // lstm_hidden 64: gate columns in the order the tcgen05 recurrence wants them (4 * unit + gate per direction)
+        const bool tc_order = HS == 64;
+        auto gate_col = [&](int d, int g, int u) { return tc_order ? d * 4 * HS + u * 4 + g : d * 4 * HS + g * HS + u; };
         if (!rc) {
-            W = wf;
-            W.insert(W.end(), wr.begin(), wr.end());
+            W.assign((size_t)8 * HS * Kin, 0.f);
+            for (int d = 0; d < 2; ++d)
+                for (int g = 0; g < 4; ++g)
+                    for (int u = 0; u < HS; ++u)
+                        memcpy(&W[(size_t)gate_col(d, g, u) * Kin], &(d ? wr : wf)[(size_t)(g * HS + u) * Kin],
+                               (size_t)Kin * sizeof(float));
             rc = upload_split_weight(W, 8 * HS, Kin, &h->wih[layer]);
         }
         if (!rc) rc = download(pbif, 4 * HS, bif);
@@ -723,7 +753,11 @@ int cbas_b200_head_create(const cbas_head_cfg* cfg, const cbas_head_weights* w, 
         if (!rc) rc = download(pbhr, 4 * HS, bhr);
         if (!rc) {
             W.assign(8 * HS, 0.f);
-            for (int i = 0; i < 4 * HS; ++i) { W[i] = bif[i] + bhf[i]; W[4 * HS + i] = bir[i] + bhr[i]; }
+            for (int g = 0; g < 4; ++g)
+                for (int u = 0; u < HS; ++u) {
+                    W[gate_col(0, g, u)] = bif[g * HS + u] + bhf[g * HS + u];
+                    W[gate_col(1, g, u)] = bir[g * HS + u] + bhr[g * HS + u];
+                }
             rc = upload_f32(W, &h->bg[layer]);
         }
         // recurrent weights: Wt[dir][k][unit][gate] = W_hh[dir][gate*Hs + unit][k]
@@ -740,6 +774,25 @@ int cbas_b200_head_create(const cbas_head_cfg* cfg, const cbas_head_weights* w, 
                             W[(((size_t)d * HS + k) * HS + u) * 4 + g] = S[(size_t)(g * HS + u) * HS + k];
             }
             rc = upload_f32(W, &h->whh_t[layer]);
+        }
+        if (!rc && tc_order) {
+            // [dir][hi, lo][column 4 * unit + gate][k] bf16 for head_lstm_tc_kernel
+            std::vector<uint16_t> B((size_t)2 * 2 * 4 * HS * HS);
+            for (int d = 0; d < 2; ++d) {
+                const std::vector<float>& S = d ? hr : hf;
+                for (int g = 0; g < 4; ++g)
+                    for (int u = 0; u < HS; ++u)
+                        for (int k = 0; k < HS; ++k) {
+                            const float w = S[(size_t)(g * HS + u) * HS + k];
+                            const uint16_t hi = f2bf(w), lo = f2bf(w - bf2f(hi));
+                            const size_t col = (size_t)u * 4 + g;
+                            B[(((size_t)d * 2 + 0) * 4 * HS + col) * HS + k] = hi;
+                            B[(((size_t)d * 2 + 1) * 4 * HS + col) * HS + k] = lo;
+                        }
+            }
+            rc = check_cuda(cudaMalloc((void**)&h->whh_tc[layer], B.size() * 2), "head weights");
+            if (!rc) rc = check_cuda(cudaMemcpy(h->whh_tc[layer], B.data(), B.size() * 2, cudaMemcpyHostToDevice),
+                                     "recurrent weight upload");
         }
     }
     if (!rc) rc = download(w->lin1_w, (size_t)C * F, W);
@@ -759,16 +812,10 @@ int cbas_b200_head_create(const cbas_head_cfg* cfg, const cbas_head_weights* w, 
         h->inv_att_temp = (float)(1.0 / (sp + 1e-3));
         h->gate_sig = (float)(1.0 / (1.0 + std::exp(-(double)w->gate)));
     }
-    // chunk workspace
-    const size_t rows = (size_t)h->chunk_windows * T;
-    if (!rc) rc = check_cuda(cudaMalloc((void**)&h->A, rows * 1152 * 2), "head workspace");
-    if (!rc) rc = check_cuda(cudaMalloc((void**)&h->Z, rows * HEAD_LIN0 * 4), "head workspace");
-    if (!rc) rc = check_cuda(cudaMalloc((void**)&h->G, rows * 8 * HS * 4), "head workspace");
-    if (!rc && cfg->lstm_layers == 2) rc = check_cuda(cudaMalloc((void**)&h->H0, rows * 2 * HS * 4), "head workspace");
-    if (!rc) rc = check_cuda(cudaMalloc((void**)&h->H, (size_t)h->chunk_windows * (h->r - h->l) * 2 * HS * 4), "head workspace");
-    if (!rc) rc = check_cuda(cudaMalloc((void**)&h->lin, (size_t)h->chunk_windows * C * 4), "head workspace");
-    if (!rc) rc = check_cuda(cudaFuncSetAttribute(head_lstm_dir_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  lstm_smem_bytes(64, true)), "lstm smem attribute");
+    // (the chunk workspace is allocated by head_ensure_chunk_ws on the first run, sized to the work)
+    if (!rc && HS != 64)
+        rc = check_cuda(cudaFuncSetAttribute(head_lstm_dir_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             lstm_smem_bytes(128, false)), "lstm smem attribute");
     if (rc) { cbas_b200_head_destroy(h); return rc; }
     *out = h;
     return 0;
@@ -779,7 +826,7 @@ void cbas_b200_head_destroy(cbas_head* h) {
     DeviceGuard guard(h->device);
     head_free_ws(h);
     cudaFree(h->wp); cudaFree(h->w0); cudaFree(h->b3); cudaFree(h->ln_g); cudaFree(h->ln_b); cudaFree(h->b0);
-    for (int i = 0; i < 2; ++i) { cudaFree(h->wih[i]); cudaFree(h->bg[i]); cudaFree(h->whh_t[i]); }
+    for (int i = 0; i < 2; ++i) { cudaFree(h->wih[i]); cudaFree(h->bg[i]); cudaFree(h->whh_t[i]); cudaFree(h->whh_tc[i]); }
     cudaFree(h->H0); cudaFree(h->lin1_w); cudaFree(h->lin1_b);
     cudaFree(h->lin2_w); cudaFree(h->lin2_b); cudaFree(h->att_w);
     cudaFree(h->A); cudaFree(h->Z); cudaFree(h->G); cudaFree(h->H); cudaFree(h->lin);
@@ -812,8 +859,10 @@ static int head_run(cbas_head* h, const void* x_dev, bool x_is_f16, long long n_
     }
     const float inv_temp = 1.0f / (temperature > 1e-3f ? temperature : 1e-3f);
     const int n_keep = h->r - h->l;
-    for (long long w0 = 0; w0 < n_windows; w0 += h->chunk_windows) {
-        const int nw = (int)((n_windows - w0) < h->chunk_windows ? (n_windows - w0) : h->chunk_windows);
+    const int chunk = (int)(n_windows < h->max_chunk_windows ? n_windows : h->max_chunk_windows);
+    if (int rc = head_ensure_chunk_ws(h, chunk)) return rc;
+    for (long long w0 = 0; w0 < n_windows; w0 += chunk) {
+        const int nw = (int)((n_windows - w0) < chunk ? (n_windows - w0) : chunk);
         const int rows = nw * T;
         {
             ProfScope prof(PROF_HEAD_FEATURES, s);
@@ -838,14 +887,23 @@ static int head_run(cbas_head* h, const void* x_dev, bool x_is_f16, long long n_
         const int HS = h->cfg.lstm_hidden, layers = h->cfg.lstm_layers;
         auto run_lstm = [&](int layer, int keep_l, int keep_r, float* Hout) -> int {
             ProfScope prof(PROF_HEAD_LSTM, s);
+            if (HS == 64) {
+                // persistent tcgen05 recurrence: one CTA per SM and direction, two 128-window tiles in flight per CTA
+                static DeviceSmemOptIn optin;
+                CBAS_CHECK(optin.ensure(head_lstm_tc_kernel, HLT_SMEM_BYTES));
+                CUtensorMap tg;
+                if (int rc = make_tmap_3d_f32(&tg, h->G, 512, T, nw, 2048, (long long)T * 2048, 32, 1, 128)) return rc;
+                const int pairs = ((nw + 127) / 128 + 1) / 2, per_dir = sm_count() / 2 > 0 ? sm_count() / 2 : 1;
+                dim3 grid(pairs < per_dir ? pairs : per_dir, 2);
+                head_lstm_tc_kernel<<<grid, HLT_THREADS, HLT_SMEM_BYTES, s>>>(tg, h->whh_tc[layer], nw, T, keep_l, keep_r,
+                                                                            Hout);
+                count_launch();
+                return check_cuda(cudaGetLastError(), "head_lstm_tc_kernel launch");
+            }
             const int per_cta = LSTM_WARPS * LSTM_WPW;
             dim3 grid((nw + per_cta - 1) / per_cta, 2);
-            if (HS == 64)
-                head_lstm_dir_kernel<64, true><<<grid, LSTM_WARPS * 32, lstm_smem_bytes(64, true), s>>>(
-                    h->G, h->whh_t[layer], nw, T, keep_l, keep_r, Hout);
-            else
-                head_lstm_dir_kernel<128, false><<<grid, LSTM_WARPS * 32, lstm_smem_bytes(128, false), s>>>(
-                    h->G, h->whh_t[layer], nw, T, keep_l, keep_r, Hout);
+            head_lstm_dir_kernel<128, false><<<grid, LSTM_WARPS * 32, lstm_smem_bytes(128, false), s>>>(
+                h->G, h->whh_t[layer], nw, T, keep_l, keep_r, Hout);
             count_launch();
             return check_cuda(cudaGetLastError(), "head_lstm_dir_kernel launch");
         };

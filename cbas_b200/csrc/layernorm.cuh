@@ -12,12 +12,13 @@ namespace cbas {
 template <int D, typename OutT>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ in, long long in_row_stride, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, OutT* __restrict__ out, int rows, float eps) {
+                 const float* __restrict__ beta, OutT* __restrict__ out, int rows, float eps, int reverse) {
     static_assert(D % 128 == 0, "D must be a multiple of 128");
     constexpr int V = D / 128;  // float4 per lane
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
+    if (reverse) warp = rows - 1 - warp;  // last rows first: the ones the preceding kernel left in L2
     const float4* src = reinterpret_cast<const float4*>(in + (long long)warp * in_row_stride * D);
     float4 x[V];
 #pragma unroll

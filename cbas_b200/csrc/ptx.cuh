@@ -79,6 +79,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* desc, ui
         : "memory");
 }
 
+// 3-D tiled load global -> shared
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // 2-D tiled store shared -> global (bulk async group), and the same with an fp32 add-reduction in L2.
 __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int crd_inner, int crd_outer) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

@@ -395,6 +395,9 @@ class DinoEncoder(nn.Module):
             env = os.environ.get("CBAS_B200_LN_FUSION")  # A/B timing: 0 = standalone LayerNorm kernels, 1 = fused
             if env is not None and _lib.OPT_LN_FUSION not in self._options:
                 nat.set_option(_lib.OPT_LN_FUSION, int(env))
+            env = os.environ.get("CBAS_B200_SERPENTINE")  # A/B timing: 0 = every kernel walks the rows ascending
+            if env is not None and _lib.OPT_SERPENTINE not in self._options:
+                nat.set_option(_lib.OPT_SERPENTINE, int(env))
             for opt, val in self._options.items():
                 nat.set_option(opt, val)
             self._native[key] = nat

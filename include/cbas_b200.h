@@ -104,6 +104,9 @@ void cbas_b200_encoder_destroy(cbas_encoder* enc);
                                        1 = general shared-memory tiled kernel, 0 = per-pixel kernel                 */
 #define CBAS_OPT_LN_FUSION 3        /* 1 = norm1 / norm2 fused into the GEMMs around them (csrc/gemm_tcgen05.cuh),
                                        0 = standalone LayerNorm kernels between the GEMMs (one HBM pass each)       */
+#define CBAS_OPT_SERPENTINE 4       /* standalone-LayerNorm path: 1 (default) = consecutive kernels of a block walk the rows
+                                       in opposite directions (each starts on what its predecessor left in L2), 0 = all
+                                       ascending                                                                    */
 int cbas_b200_encoder_set_option(cbas_encoder* enc, int32_t option, int32_t value);
 
 /* frames_dev: uint8 RGB HWC (what decord's get_batch(...).asnumpy() yields, cbas.py:425), n frames,
