@@ -97,7 +97,7 @@ template <int BLOCK_N, int CG>
 int launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, const GemmParams& p, int epi,
               cudaStream_t stream) {
     CUtensorMap ta, tb;
-    if (int rc = make_tmap(&ta, A, false, p.M, p.K, lda, GEMM_BLOCK_K, GEMM_BLOCK_M)) return rc;
+    if (int rc = make_tmap(&ta, A, false, p.M, p.a_wrap ? p.a_wrap : p.K, lda, GEMM_BLOCK_K, GEMM_BLOCK_M)) return rc;
     if (int rc = make_tmap(&tb, W, false, p.N, p.K, ldw, GEMM_BLOCK_K, BLOCK_N / CG)) return rc;
     switch (epi) {
         case EPI_BIAS_BF16: return launch_one<BLOCK_N, EPI_BIAS_BF16, CG>(ta, tb, p, stream);
@@ -124,6 +124,8 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
     if (p.M <= 0) return 0;
     ProfScope prof(prof_tag, stream);
     if (p.K % GEMM_BLOCK_K != 0 || p.K <= 0) return fail("GEMM K must be a positive multiple of 64");
+    if (p.a_wrap && (p.a_wrap % GEMM_BLOCK_K != 0 || p.a_wrap <= 0 || 2 * p.K != 3 * p.a_wrap))
+        return fail("GEMM a_wrap must be a multiple of 64 with K = 1.5 * a_wrap");
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) || (lda % 8) || (ldw % 8))
         return fail("GEMM operands must be 16-byte aligned with row pitch a multiple of 8 elements");
     // CTA pairs (256-row tiles) whenever there is enough work to fill the chip with them

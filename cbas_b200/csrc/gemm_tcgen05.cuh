@@ -91,6 +91,9 @@ struct GemmParams {
     float ln_eps;
     void* hb;
     int ldhb;
+    // split-bf16 GEMMs (head.cu): A holds [hi | lo] (a_wrap columns) while K = 1.5 * a_wrap; K blocks at or past
+    // a_wrap read A from column k - a_wrap again (hi * W_lo).  0 = A is K wide.
+    int a_wrap;
     // walk the row blocks from the last to the first (encoder.cu: consecutive kernels alternate direction, so each one
     // starts on the rows its predecessor touched last, which are still in L2).  Not supported by the LN producers.
     int reverse;
@@ -222,17 +225,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int b_row = n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / CG);
             for (int kb = 0; kb < k_blocks; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
+                const int a_col = p.a_wrap && kb * GEMM_BLOCK_K >= p.a_wrap ? kb * GEMM_BLOCK_K - p.a_wrap : kb * GEMM_BLOCK_K;
                 if (elect_one()) {
                     if (CG == 1) {
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
-                        tma_load_2d(smem_a + stage * Cfg::kStageA, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, a_row);
+                        tma_load_2d(smem_a + stage * Cfg::kStageA, &tmap_a, &full_bar[stage], a_col, a_row);
                         tma_load_2d(smem_b + stage * Cfg::kStageB, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, b_row);
                     } else {
                         // the leader's barrier counts the bytes of BOTH CTAs' loads
                         if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStage);
                         else mbar_arrive_cluster(&full_bar[stage], 0);
-                        tma_load_2d_pair(smem_a + stage * Cfg::kStageA, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K,
-                                         a_row);
+                        tma_load_2d_pair(smem_a + stage * Cfg::kStageA, &tmap_a, &full_bar[stage], a_col, a_row);
                         tma_load_2d_pair(smem_b + stage * Cfg::kStageB, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K,
                                          b_row);
                     }

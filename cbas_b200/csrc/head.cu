@@ -5,7 +5,7 @@
 // The reference builds every window on the host ([512,31,768] fp32 per batch, each embedding row shipped 31x)
 // and runs ~40 small launches per batch.  Here the per-frame work is hoisted out of the windows:
 //
-//   H1 head_split_embed   f16 embeddings -> exact bf16 hi/lo split [n, 3F]; per-frame lin1 logits q = W1 x (fp32)
+//   H1 head_split_embed   f16 embeddings -> exact bf16 hi/lo split [n, 2F]; per-frame lin1 logits q = W1 x (fp32)
 //   H2 tcgen05 GEMM       P[n,384] = x (Wc|Wd|Wa)^T   - EMA, deltas and lin1 are linear, so the three 768->128
 //                         bottleneck projections are taken ONCE per frame and the EMA / delta / acceleration
 //                         recurrences run in the 128-d projected space (verified identity)
@@ -28,7 +28,8 @@
 //                         lerp with the linear branch, temperature softmax
 //
 // GEMM precision: the reference head is fp32.  Operands are split into bf16 hi + lo parts and the product is
-// taken as hi*hi + lo*hi + hi*lo (K tripled, fp32 accumulation in TMEM), which keeps ~16 mantissa bits per
+// taken as hi*hi + lo*hi + hi*lo (K tripled: activations are stored [hi | lo] and the GEMM's third K block re-reads
+// hi, GemmParams::a_wrap; weights are [hi | hi | lo]; fp32 accumulation in TMEM), which keeps ~16 mantissa bits per
 // factor - three orders of magnitude inside the 1e-3 probability gate - while staying on the tensor cores.
 #include "../../include/cbas_b200.h"
 #include "common.h"
@@ -61,7 +62,7 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 }
 
 // ---------------------------------------------------------------------------------------------- H1
-// one warp per frame.  x' = [hi | lo | hi] (3F bf16);  q[f][c] = sum_k lin1_w[c][k] x[k]
+// one warp per frame.  x' = [hi | lo] (2F bf16; the GEMM re-reads hi for its third K block, GemmParams::a_wrap);  q[f][c] = sum_k lin1_w[c][k] x[k]
 template <typename InT>  // __half: the stored `cls` rows (split exact); float: forward(x) windows (16-bit split)
 __global__ void __launch_bounds__(256)
 head_split_embed_kernel(const InT* __restrict__ emb, long long n, int F, __nv_bfloat16* __restrict__ xs,
@@ -70,7 +71,7 @@ head_split_embed_kernel(const InT* __restrict__ emb, long long n, int F, __nv_bf
     const int lane = threadIdx.x & 31;
     if (f >= n) return;
     const InT* x = emb + f * F;
-    __nv_bfloat16* o = xs + f * 3 * F;
+    __nv_bfloat16* o = xs + f * 2 * F;
     float acc[HEAD_MAX_C];
 #pragma unroll
     for (int c = 0; c < HEAD_MAX_C; ++c) acc[c] = 0.f;
@@ -85,7 +86,6 @@ head_split_embed_kernel(const InT* __restrict__ emb, long long n, int F, __nv_bf
         hi.x = h0; hi.y = h1; lo.x = l0; lo.y = l1;
         *reinterpret_cast<__nv_bfloat162*>(o + k) = hi;
         *reinterpret_cast<__nv_bfloat162*>(o + F + k) = lo;
-        *reinterpret_cast<__nv_bfloat162*>(o + 2 * F + k) = hi;
 #pragma unroll
         for (int c = 0; c < HEAD_MAX_C; ++c) {
             if (c < C) {
@@ -118,7 +118,7 @@ struct FeatParams {
     const float* ln_b;   // [384]
     const float* lin1_b; // [C]
     int C;
-    __nv_bfloat16* A;    // [windows*T, 1152] = [hi(384) | lo(384) | hi(384)]
+    __nv_bfloat16* A;    // [T*windows, 768] = [hi(384) | lo(384)], row = t * windows + window
     float* lin_logits;   // [windows, C]
 };
 
@@ -127,7 +127,8 @@ __device__ __forceinline__ void feat_emit(const float (&v)[4], int stream, int l
     // v = 4 channels (lane*4..) of one stream before bias; GELU, LayerNorm over the 128 channels of the stream
     const int ch = stream * HEAD_BN + lane * 4;
     const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
-    float y[4] = {gelu_erf(v[0] + b.x), gelu_erf(v[1] + b.y), gelu_erf(v[2] + b.z), gelu_erf(v[3] + b.w)};
+    float y[4] = {gelu_erf_fast<5>(v[0] + b.x), gelu_erf_fast<5>(v[1] + b.y), gelu_erf_fast<5>(v[2] + b.z),
+                  gelu_erf_fast<5>(v[3] + b.w)};
     const float mean = warp_sum((y[0] + y[1]) + (y[2] + y[3])) * (1.0f / HEAD_BN);
     float d[4] = {y[0] - mean, y[1] - mean, y[2] - mean, y[3] - mean};
     const float var = warp_sum((d[0] * d[0] + d[1] * d[1]) + (d[2] * d[2] + d[3] * d[3])) * (1.0f / HEAD_BN);
@@ -146,7 +147,6 @@ __device__ __forceinline__ void feat_emit(const float (&v)[4], int stream, int l
     ul.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
     *reinterpret_cast<uint2*>(row + ch) = uh;
     *reinterpret_cast<uint2*>(row + 384 + ch) = ul;
-    *reinterpret_cast<uint2*>(row + 768 + ch) = uh;
 }
 
 // one warp per window; lane owns channels lane*4..+3 of each of the three streams and (lane < C) one q channel
@@ -156,7 +156,8 @@ head_features_kernel(const FeatParams p) {
     const int lane = threadIdx.x & 31;
     if (wl >= p.windows) return;
     const long long f = p.w0 + wl * p.stride;
-    __nv_bfloat16* rows = p.A + (long long)wl * p.T * 1152;
+    __nv_bfloat16* rows = p.A + (long long)wl * 768;  // row of (window, t) = t * windows + window
+    const long long tstride = (long long)p.windows * 768;
     const float a = p.alpha;
 
     auto frame_of = [&](int t) {  // replicate padding == clamped frame index (cbas.py:512-525)
@@ -210,22 +211,22 @@ head_features_kernel(const FeatParams p) {
     feat_emit(v, 2, lane, p, rows);
     if (0 >= p.l && 0 < p.r) qsum += sq;
     // t = 1: cls = s1 ; delta = s1 - s0 ; acc = 2 (s1 - s0)
-    feat_emit(sc1, 0, lane, p, rows + 1152);
+    feat_emit(sc1, 0, lane, p, rows + tstride);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = sd1[i] - sd0[i];
-    feat_emit(v, 1, lane, p, rows + 1152);
+    feat_emit(v, 1, lane, p, rows + tstride);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = 2.0f * (sa1[i] - sa0[i]);
-    feat_emit(v, 2, lane, p, rows + 1152);
+    feat_emit(v, 2, lane, p, rows + tstride);
     if (1 >= p.l && 1 < p.r) qsum += sq1;
     // t = 2: cls = s2 ; delta = s2 - s1 ; acc = s2 - 2 s1 + s0
-    feat_emit(sc2, 0, lane, p, rows + 2 * 1152);
+    feat_emit(sc2, 0, lane, p, rows + 2 * tstride);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = sd2[i] - sd1[i];
-    feat_emit(v, 1, lane, p, rows + 2 * 1152);
+    feat_emit(v, 1, lane, p, rows + 2 * tstride);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = sa2[i] - 2.0f * sa1[i] + sa0[i];
-    feat_emit(v, 2, lane, p, rows + 2 * 1152);
+    feat_emit(v, 2, lane, p, rows + 2 * tstride);
     if (2 >= p.l && 2 < p.r) qsum += sq2;
 
     // t >= 3: roll the states (cur = s_{t-1}, prev = s_{t-2})
@@ -246,7 +247,7 @@ head_features_kernel(const FeatParams p) {
             an[i] = acur[i] + a * (xa[i] - acur[i]);
         }
         qcur = qcur + a * (xq - qcur);
-        __nv_bfloat16* row = rows + (long long)t * 1152;
+        __nv_bfloat16* row = rows + t * tstride;
         feat_emit(cn, 0, lane, p, row);
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = dn[i] - dcur[i];
@@ -273,20 +274,21 @@ head_center_split_kernel(const float* __restrict__ Z, int windows, int T, __nv_b
     const int wl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wl >= windows) return;
-    const float* z = Z + (long long)wl * T * HEAD_LIN0 + lane * 8;
+    const float* z = Z + (long long)wl * HEAD_LIN0 + lane * 8;  // rows are t-major: row = t * windows + window
+    const long long zs = (long long)windows * HEAD_LIN0;
     float m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int t = 0; t < T; ++t) {
-        const float4 a = *reinterpret_cast<const float4*>(z + (long long)t * HEAD_LIN0);
-        const float4 b = *reinterpret_cast<const float4*>(z + (long long)t * HEAD_LIN0 + 4);
+        const float4 a = *reinterpret_cast<const float4*>(z + t * zs);
+        const float4 b = *reinterpret_cast<const float4*>(z + t * zs + 4);
         m[0] += a.x; m[1] += a.y; m[2] += a.z; m[3] += a.w; m[4] += b.x; m[5] += b.y; m[6] += b.z; m[7] += b.w;
     }
     const float inv = 1.0f / (float)T;
 #pragma unroll
     for (int i = 0; i < 8; ++i) m[i] *= inv;
-    __nv_bfloat16* o = Zs + (long long)wl * T * 768 + lane * 8;
+    __nv_bfloat16* o = Zs + (long long)wl * 512 + lane * 8;
     for (int t = 0; t < T; ++t) {
-        const float4 a = *reinterpret_cast<const float4*>(z + (long long)t * HEAD_LIN0);
-        const float4 b = *reinterpret_cast<const float4*>(z + (long long)t * HEAD_LIN0 + 4);
+        const float4 a = *reinterpret_cast<const float4*>(z + t * zs);
+        const float4 b = *reinterpret_cast<const float4*>(z + t * zs + 4);
         const float x[8] = {a.x - m[0], a.y - m[1], a.z - m[2], a.w - m[3], b.x - m[4], b.y - m[5], b.z - m[6], b.w - m[7]};
         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -297,10 +299,9 @@ head_center_split_kernel(const float* __restrict__ Z, int windows, int T, __nv_b
             hi[i >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
             lo[i >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
         }
-        __nv_bfloat16* r = o + (long long)t * 768;
+        __nv_bfloat16* r = o + (long long)t * windows * 512;
         *reinterpret_cast<uint4*>(r) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(r + 256) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(r + 512) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     }
 }
 
@@ -318,9 +319,10 @@ constexpr int lstm_smem_bytes(int HS, bool resident) {
 // the reads are L1 hits after the first warp).
 template <int HS, bool RESIDENT>
 __global__ void __launch_bounds__(LSTM_WARPS * 32)
-head_lstm_dir_kernel(const float* __restrict__ G,        // [windows*T, 8*HS] input gates (fwd | rev), biases included
+head_lstm_dir_kernel(const float* __restrict__ Gf,       // [r * windows, 4*HS] input gates of the forward direction, row = t * windows + window
+                     const float* __restrict__ Gr,       // [(T - l) * windows, 4*HS] ... of the reverse direction, row = (t - l) * windows + window
                      const float* __restrict__ whh_t,    // [2][HS k][HS unit][4 gate]
-                     int windows, int T, int l, int r,
+                     int windows, int T, int l, int r, int hout_t_major,
                      float* __restrict__ Hout) {         // [windows, r-l, 2*HS] (fwd | rev)
     constexpr int UPL = HS / 32;  // hidden units per lane
     extern __shared__ __align__(16) uint8_t lstm_smem[];
@@ -353,7 +355,7 @@ head_lstm_dir_kernel(const float* __restrict__ G,        // [windows*T, 8*HS] in
 #pragma unroll
         for (int w = 0; w < LSTM_WPW; ++w) {
             const int win = min(w_base + w, windows - 1);
-            const float* g = G + ((long long)win * T + t) * (8 * HS) + dir * 4 * HS;
+            const float* g = (dir ? Gr : Gf) + ((long long)(dir ? t - l : t) * windows + win) * (4 * HS);
 #pragma unroll
             for (int u = 0; u < UPL; ++u)
 #pragma unroll
@@ -393,7 +395,8 @@ head_lstm_dir_kernel(const float* __restrict__ G,        // [windows*T, 8*HS] in
 #pragma unroll
             for (int w = 0; w < LSTM_WPW; ++w) {
                 if (w_base + w < windows) {
-                    float* o = Hout + ((long long)(w_base + w) * n_keep + (t - l)) * (2 * HS) + dir * HS;
+                    float* o = Hout + (hout_t_major ? (long long)(t - l) * windows + (w_base + w)
+                                                    : (long long)(w_base + w) * n_keep + (t - l)) * (2 * HS) + dir * HS;
 #pragma unroll
                     for (int u = 0; u < UPL; ++u) o[lane + 32 * u] = hn[u][w];
                 }
@@ -403,7 +406,7 @@ head_lstm_dir_kernel(const float* __restrict__ G,        // [windows*T, 8*HS] in
     }
 }
 
-// fp32 rows -> bf16 [hi | lo | hi] (the A-operand layout of the split GEMMs); K multiple of 4
+// fp32 rows -> bf16 [hi | lo] (the A-operand layout of the split GEMMs); K multiple of 4
 __global__ void __launch_bounds__(256)
 head_split_rows_kernel(const float* __restrict__ X, long long rows, int K, __nv_bfloat16* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 per thread
@@ -416,10 +419,9 @@ head_split_rows_kernel(const float* __restrict__ X, long long rows, int K, __nv_
     __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) split_bf16(x[j], hi[j], lo[j]);
-    __nv_bfloat16* o = out + row * 3 * K + k;
+    __nv_bfloat16* o = out + row * 2 * K + k;
     *reinterpret_cast<uint2*>(o) = *reinterpret_cast<uint2*>(hi);
     *reinterpret_cast<uint2*>(o + K) = *reinterpret_cast<uint2*>(lo);
-    *reinterpret_cast<uint2*>(o + 2 * K) = *reinterpret_cast<uint2*>(hi);
 }
 
 // ---------------------------------------------------------------------------------------------- H8
@@ -645,7 +647,7 @@ int head_ensure_ws(cbas_head* h, long long n) {
     if (n <= h->cap_frames) return 0;
     head_free_ws(h);
     const int F = h->cfg.in_features, C = h->cfg.out_features;
-    CBAS_CHECK(cudaMalloc((void**)&h->xs, (size_t)n * 3 * F * 2));
+    CBAS_CHECK(cudaMalloc((void**)&h->xs, (size_t)n * 2 * F * 2));
     CBAS_CHECK(cudaMalloc((void**)&h->P, (size_t)n * 384 * 4));
     CBAS_CHECK(cudaMalloc((void**)&h->q, (size_t)n * C * 4));
     h->cap_frames = n;
@@ -659,7 +661,7 @@ int head_ensure_chunk_ws(cbas_head* h, int windows) {
     h->chunk_windows = 0;
     const int T = h->cfg.seq_len, HS = h->cfg.lstm_hidden, C = h->cfg.out_features;
     const size_t rows = (size_t)windows * T;
-    CBAS_CHECK(cudaMalloc((void**)&h->A, rows * 1152 * 2));
+    CBAS_CHECK(cudaMalloc((void**)&h->A, rows * 768 * 2));
     CBAS_CHECK(cudaMalloc((void**)&h->Z, rows * HEAD_LIN0 * 4));
     CBAS_CHECK(cudaMalloc((void**)&h->G, rows * 8 * HS * 4));
     if (h->cfg.lstm_layers == 2) CBAS_CHECK(cudaMalloc((void**)&h->H0, rows * 2 * HS * 4));
@@ -853,8 +855,8 @@ static int head_run(cbas_head* h, const void* x_dev, bool x_is_f16, long long n_
     for (long long f0 = 0; f0 < n_frames; f0 += (1 << 20)) {  // the GEMM takes int M
         const int m = (int)((n_frames - f0) < (1 << 20) ? (n_frames - f0) : (1 << 20));
         GemmParams p{};
-        p.M = m; p.N = 3 * HEAD_BN; p.K = 3 * F; p.bias = nullptr; p.out = h->P + f0 * 384; p.ldo = 384;
-        if (int rc = launch_gemm(h->xs + f0 * 3 * F, 3 * F, h->wp, 3 * F, p, EPI_BIAS_F32, s, PROF_HEAD_PROJ_GEMM))
+        p.M = m; p.N = 3 * HEAD_BN; p.K = 3 * F; p.a_wrap = 2 * F; p.bias = nullptr; p.out = h->P + f0 * 384; p.ldo = 384;
+        if (int rc = launch_gemm(h->xs + f0 * 2 * F, 2 * F, h->wp, 3 * F, p, EPI_BIAS_F32, s, PROF_HEAD_PROJ_GEMM))
             return rc;
     }
     const float inv_temp = 1.0f / (temperature > 1e-3f ? temperature : 1e-3f);
@@ -874,8 +876,8 @@ static int head_run(cbas_head* h, const void* x_dev, bool x_is_f16, long long n_
         }
         {
             GemmParams p{};
-            p.M = rows; p.N = HEAD_LIN0; p.K = 1152; p.bias = h->b0; p.out = h->Z; p.ldo = HEAD_LIN0;
-            if (int rc = launch_gemm(h->A, 1152, h->w0, 1152, p, EPI_BIAS_GELU_F32, s, PROF_HEAD_LIN0_GEMM)) return rc;
+            p.M = rows; p.N = HEAD_LIN0; p.K = 1152; p.a_wrap = 768; p.bias = h->b0; p.out = h->Z; p.ldo = HEAD_LIN0;
+            if (int rc = launch_gemm(h->A, 768, h->w0, 1152, p, EPI_BIAS_GELU_F32, s, PROF_HEAD_LIN0_GEMM)) return rc;
         }
         __nv_bfloat16* Zs = h->A;  // A is dead after the lin0 GEMM: reuse it for the split, centred z
         {
@@ -885,36 +887,50 @@ static int head_run(cbas_head* h, const void* x_dev, bool x_is_f16, long long n_
             if (int rc = check_cuda(cudaGetLastError(), "head_center_split_kernel launch")) return rc;
         }
         const int HS = h->cfg.lstm_hidden, layers = h->cfg.lstm_layers;
-        auto run_lstm = [&](int layer, int keep_l, int keep_r, float* Hout) -> int {
+        // One LSTM layer: the input half of the gates for the steps each direction actually runs (forward: t < keep_r,
+        // reverse: t >= keep_l - rows are t-major, so both are contiguous row ranges of X), then the recurrence.
+        //   X: [T * nw, a_wrap] bf16 [hi | lo];  Gf = G, Gr = G + keep_r * nw * 4HS
+        auto run_lstm = [&](int layer, const __nv_bfloat16* X, int a_wrap, int keep_l, int keep_r, bool hout_t_major,
+                            float* Hout) -> int {
+            const int K3 = a_wrap / 2 * 3;
+            float* Gf = h->G;
+            float* Gr = h->G + (size_t)keep_r * nw * 4 * HS;
+            for (int d = 0; d < 2; ++d) {
+                GemmParams p{};
+                p.M = (d ? T - keep_l : keep_r) * nw; p.N = 4 * HS; p.K = K3; p.a_wrap = a_wrap;
+                p.bias = h->bg[layer] + d * 4 * HS; p.out = d ? Gr : Gf; p.ldo = 4 * HS;
+                const __nv_bfloat16* A = X + (d ? (size_t)keep_l * nw * a_wrap : 0);
+                if (int rc = launch_gemm(A, a_wrap, h->wih[layer] + (size_t)d * 4 * HS * K3, K3, p, EPI_BIAS_F32, s,
+                                         PROF_HEAD_IH_GEMM)) return rc;
+            }
             ProfScope prof(PROF_HEAD_LSTM, s);
             if (HS == 64) {
                 // persistent tcgen05 recurrence: one CTA per SM and direction, two 128-window tiles in flight per CTA
                 static DeviceSmemOptIn optin;
                 CBAS_CHECK(optin.ensure(head_lstm_tc_kernel, HLT_SMEM_BYTES));
-                CUtensorMap tg;
-                if (int rc = make_tmap_3d_f32(&tg, h->G, 512, T, nw, 2048, (long long)T * 2048, 32, 1, 128)) return rc;
+                CUtensorMap tgf, tgr;  // G of a direction as [steps][windows][256], box {32, 128, 1}
+                if (int rc = make_tmap_3d_f32(&tgf, Gf, 256, nw, keep_r, 1024, (long long)nw * 1024, 32, 128, 1)) return rc;
+                if (int rc = make_tmap_3d_f32(&tgr, Gr, 256, nw, T - keep_l, 1024, (long long)nw * 1024, 32, 128, 1)) return rc;
                 const int pairs = ((nw + 127) / 128 + 1) / 2, per_dir = sm_count() / 2 > 0 ? sm_count() / 2 : 1;
                 dim3 grid(pairs < per_dir ? pairs : per_dir, 2);
-                head_lstm_tc_kernel<<<grid, HLT_THREADS, HLT_SMEM_BYTES, s>>>(tg, h->whh_tc[layer], nw, T, keep_l, keep_r,
-                                                                            Hout);
+                head_lstm_tc_kernel<<<grid, HLT_THREADS, HLT_SMEM_BYTES, s>>>(tgf, tgr, h->whh_tc[layer], nw, T, keep_l, keep_r,
+                                                                            hout_t_major ? 1 : 0, Hout);
                 count_launch();
                 return check_cuda(cudaGetLastError(), "head_lstm_tc_kernel launch");
             }
             const int per_cta = LSTM_WARPS * LSTM_WPW;
             dim3 grid((nw + per_cta - 1) / per_cta, 2);
             head_lstm_dir_kernel<128, false><<<grid, LSTM_WARPS * 32, lstm_smem_bytes(128, false), s>>>(
-                h->G, h->whh_t[layer], nw, T, keep_l, keep_r, Hout);
+                Gf, Gr, h->whh_t[layer], nw, T, keep_l, keep_r, hout_t_major ? 1 : 0, Hout);
             count_launch();
             return check_cuda(cudaGetLastError(), "head_lstm_dir_kernel launch");
         };
-        {
-            GemmParams p{};
-            p.M = rows; p.N = 8 * HS; p.K = 768; p.bias = h->bg[0]; p.out = h->G; p.ldo = 8 * HS;
-            if (int rc = launch_gemm(Zs, 768, h->wih[0], 768, p, EPI_BIAS_F32, s, PROF_HEAD_IH_GEMM)) return rc;
-        }
+        const __nv_bfloat16* X = Zs;
+        int x_wrap = 2 * HEAD_LIN0;
         if (layers == 2) {
-            // layer 0 over every step, then its [fwd | rev] outputs are the next layer's inputs (nn.LSTM stacking)
-            if (int rc = run_lstm(0, 0, T, h->H0)) return rc;
+            // layer 0 over every step (outputs t-major like its inputs), then its [fwd | rev] outputs are the next layer's
+            // inputs (nn.LSTM stacking)
+            if (int rc = run_lstm(0, X, x_wrap, 0, T, true, h->H0)) return rc;
             {
                 ProfScope prof(PROF_HEAD_CENTER, s);
                 const long long quads = (long long)rows * (2 * HS / 4);
@@ -922,11 +938,10 @@ static int head_run(cbas_head* h, const void* x_dev, bool x_is_f16, long long n_
                 count_launch();
                 if (int rc = check_cuda(cudaGetLastError(), "head_split_rows_kernel launch")) return rc;
             }
-            GemmParams p{};
-            p.M = rows; p.N = 8 * HS; p.K = 6 * HS; p.bias = h->bg[1]; p.out = h->G; p.ldo = 8 * HS;
-            if (int rc = launch_gemm(h->A, 6 * HS, h->wih[1], 6 * HS, p, EPI_BIAS_F32, s, PROF_HEAD_IH_GEMM)) return rc;
+            X = h->A;
+            x_wrap = 4 * HS;
         }
-        if (int rc = run_lstm(layers - 1, h->l, h->r, h->H)) return rc;
+        if (int rc = run_lstm(layers - 1, X, x_wrap, h->l, h->r, false, h->H)) return rc;
         {
             ProfScope prof(PROF_HEAD_LSTM, s);
             PoolParams pp{h->H, h->lin, nw, n_keep, C, h->att_w, h->att_b, h->inv_att_temp, h->lin2_w, h->lin2_b,

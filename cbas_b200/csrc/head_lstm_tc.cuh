@@ -13,7 +13,7 @@
 // biases), so a float4 is one cell's (i, f, g, o), and a TMA box {32 columns, 1 step, 128 windows} = 16 KB is the
 // input of 8 units of all 128 windows.  A row-per-thread global read of the same data (the TMEM lane = window
 // mapping) touches 32 different cache lines per warp instruction and ran 7x slower; TMA gathers the 128-byte row pieces
-// (rows are T * 2 KB apart) into a 3-stage ring per chain and the threads read them conflict-free from shared memory.
+// (rows are 1 KB apart) into a 3-stage ring per chain and the threads read them conflict-free from shared memory.
 //
 // Warp roles: warps 0-15 activation (chain = warp >> 3, TMEM lane quarter = warp & 3, half = (warp >> 2) & 1: a
 // thread owns one window and, of every 8-unit piece, the 4 units of its half); warps 16 / 17 MMA issue for chain
@@ -49,13 +49,15 @@ __device__ __forceinline__ float hlt_cell(float ai, float af, float ag, float ao
     return (ec - 1.f) * rcp_approx((1.f + eo) * (ec + 1.f));          // sigmoid(o) tanh(c)
 }
 
-// tmap_g: G as fp32 [windows][T][512] (columns = [fwd 256 | rev 256], 4 * unit + gate inside a direction),
-//         box {32, 1, 128}, SWIZZLE_128B, windows past the end read as zero
+// tmap_gf / tmap_gr: G of the forward / reverse direction as fp32 [steps][windows][256] (column = 4 * unit + gate; the
+//         forward array holds t = 0 .. r - 1, the reverse one t = l .. T - 1), box {32, 128, 1}, SWIZZLE_128B, windows
+//         past the end read as zero
 // whh:    [2 dir][hi, lo][256 columns (4 * unit + gate)][64 k] bf16, row-major
-// Hout:   [windows, r - l, 128] fp32 = (fwd 64 | rev 64) of the steps t in [l, r)
+// Hout:   [windows, r - l, 128] fp32 = (fwd 64 | rev 64) of the steps t in [l, r)  ([r - l, windows, 128] if hout_t_major)
 __global__ void __launch_bounds__(HLT_THREADS, 1)
-head_lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __nv_bfloat16* __restrict__ whh, int windows, int T,
-                    int l, int r, float* __restrict__ Hout) {
+head_lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_gf, const __grid_constant__ CUtensorMap tmap_gr,
+                    const __nv_bfloat16* __restrict__ whh, int windows, int T, int l, int r, int hout_t_major,
+                    float* __restrict__ Hout) {
     extern __shared__ uint8_t hlt_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(hlt_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* w_hi = smem;
@@ -88,7 +90,8 @@ head_lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __nv_bfloa
             }
         }
         fence_mbar_init();
-        tma_prefetch_desc(&tmap_g);
+        tma_prefetch_desc(&tmap_gf);
+        tma_prefetch_desc(&tmap_gr);
     }
     if (warp == HLT_ACT_WARPS) {
         tmem_alloc(tmem_slot, 512);
@@ -134,7 +137,8 @@ head_lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __nv_bfloa
                     tc_fence_after();
                 }
                 const bool keep = valid && t >= l && t < r;
-                float* ho = Hout + ((size_t)win * n_keep + (t - l)) * 128 + dir * 64 + uh * 4;
+                float* ho = Hout + (hout_t_major ? (size_t)(t - l) * windows + win : (size_t)win * n_keep + (t - l)) * 128 +
+                            dir * 64 + uh * 4;
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
                     uint32_t acc[16];
@@ -206,6 +210,8 @@ head_lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __nv_bfloa
     } else {
         // ------------------------------------------------------------------------------------ TMA producer of the chain
         uint32_t stage = 0, ephase = 1;  // a fresh barrier passes a wait on parity 1
+        const CUtensorMap* tm = dir ? &tmap_gr : &tmap_gf;
+        const int t0 = dir ? l : 0;      // first step held by this direction's array
         for (int pi = blockIdx.x; 2 * pi + chain < tiles; pi += gridDim.x) {
             const int w0 = (2 * pi + chain) * 128;
             for (int s = 0; s < steps; ++s) {
@@ -214,7 +220,7 @@ head_lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __nv_bfloa
                     mbar_wait(&g_empty[stage], ephase);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&g_full[stage], HLT_G_BYTES);
-                        tma_load_3d(g_ring + stage * HLT_G_BYTES, &tmap_g, &g_full[stage], dir * 256 + ch * 32, t, w0);
+                        tma_load_3d(g_ring + stage * HLT_G_BYTES, tm, &g_full[stage], ch * 32, w0, t - t0);
                     }
                     __syncwarp();
                     if (++stage == HLT_STAGES) { stage = 0; ephase ^= 1; }
