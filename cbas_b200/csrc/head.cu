@@ -268,40 +268,53 @@ head_features_kernel(const FeatParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------- H5
-// one warp per window: subtract the mean over the T rows of Z (fp32 mean, classifier_head.py:166-167), split.
+// Subtract the mean over the T rows of a window (fp32 mean, classifier_head.py:166-167) and split to bf16 [hi | lo].
+// Two warps per window, 128 columns each: a lane's 4 columns of all T <= CENTER_MAX_T rows stay in registers between
+// the mean and the output pass, so Z is read from HBM once (the rows of a window are a whole chunk apart).
+constexpr int CENTER_MAX_T = 32;
+template <bool RESIDENT>
 __global__ void __launch_bounds__(256)
 head_center_split_kernel(const float* __restrict__ Z, int windows, int T, __nv_bfloat16* __restrict__ Zs) {
-    const int wl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    const int wl = gw >> 1, col = (gw & 1) * 128 + lane * 4;
     if (wl >= windows) return;
-    const float* z = Z + (long long)wl * HEAD_LIN0 + lane * 8;  // rows are t-major: row = t * windows + window
+    const float* z = Z + (long long)wl * HEAD_LIN0 + col;  // rows are t-major: row = t * windows + window
     const long long zs = (long long)windows * HEAD_LIN0;
-    float m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = 0; t < T; ++t) {
-        const float4 a = *reinterpret_cast<const float4*>(z + t * zs);
-        const float4 b = *reinterpret_cast<const float4*>(z + t * zs + 4);
-        m[0] += a.x; m[1] += a.y; m[2] += a.z; m[3] += a.w; m[4] += b.x; m[5] += b.y; m[6] += b.z; m[7] += b.w;
+    float4 v[RESIDENT ? CENTER_MAX_T : 1];
+    float m[4] = {0, 0, 0, 0};
+    if constexpr (RESIDENT) {
+#pragma unroll
+        for (int t = 0; t < CENTER_MAX_T; ++t)
+            if (t < T) v[t] = __ldcs(reinterpret_cast<const float4*>(z + t * zs));
+#pragma unroll
+        for (int t = 0; t < CENTER_MAX_T; ++t)
+            if (t < T) { m[0] += v[t].x; m[1] += v[t].y; m[2] += v[t].z; m[3] += v[t].w; }
+    } else {
+        for (int t = 0; t < T; ++t) {
+            const float4 a = *reinterpret_cast<const float4*>(z + t * zs);
+            m[0] += a.x; m[1] += a.y; m[2] += a.z; m[3] += a.w;
+        }
     }
     const float inv = 1.0f / (float)T;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] *= inv;
-    __nv_bfloat16* o = Zs + (long long)wl * 512 + lane * 8;
-    for (int t = 0; t < T; ++t) {
-        const float4 a = *reinterpret_cast<const float4*>(z + t * zs);
-        const float4 b = *reinterpret_cast<const float4*>(z + t * zs + 4);
-        const float x[8] = {a.x - m[0], a.y - m[1], a.z - m[2], a.w - m[3], b.x - m[4], b.y - m[5], b.z - m[6], b.w - m[7]};
-        uint32_t hi[4], lo[4];
+    for (int i = 0; i < 4; ++i) m[i] *= inv;
+    __nv_bfloat16* o = Zs + (long long)wl * 512 + col;
+    auto emit = [&](int t, const float4& a) {
+        const float x[4] = {a.x - m[0], a.y - m[1], a.z - m[2], a.w - m[3]};
+        __nv_bfloat16 h[4], l[4];
 #pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(x[i], h0, l0);
-            split_bf16(x[i + 1], h1, l1);
-            hi[i >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lo[i >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        }
+        for (int i = 0; i < 4; ++i) split_bf16(x[i], h[i], l[i]);
         __nv_bfloat16* r = o + (long long)t * windows * 512;
-        *reinterpret_cast<uint4*>(r) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(r + 256) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint2*>(r) = *reinterpret_cast<uint2*>(h);
+        *reinterpret_cast<uint2*>(r + 256) = *reinterpret_cast<uint2*>(l);
+    };
+    if constexpr (RESIDENT) {
+#pragma unroll
+        for (int t = 0; t < CENTER_MAX_T; ++t)
+            if (t < T) emit(t, v[t]);
+    } else {
+        for (int t = 0; t < T; ++t) emit(t, *reinterpret_cast<const float4*>(z + t * zs));
     }
 }
 
@@ -882,7 +895,9 @@ static int head_run(cbas_head* h, const void* x_dev, bool x_is_f16, long long n_
         __nv_bfloat16* Zs = h->A;  // A is dead after the lin0 GEMM: reuse it for the split, centred z
         {
             ProfScope prof(PROF_HEAD_CENTER, s);
-            head_center_split_kernel<<<(nw * 32 + 255) / 256, 256, 0, s>>>(h->Z, nw, T, Zs);
+            const unsigned cgrid = (unsigned)(((long long)nw * 64 + 255) / 256);
+            if (T <= CENTER_MAX_T) head_center_split_kernel<true><<<cgrid, 256, 0, s>>>(h->Z, nw, T, Zs);
+            else head_center_split_kernel<false><<<cgrid, 256, 0, s>>>(h->Z, nw, T, Zs);
             count_launch();
             if (int rc = check_cuda(cudaGetLastError(), "head_center_split_kernel launch")) return rc;
         }
