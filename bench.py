@@ -251,6 +251,20 @@ def run_head(args, rank, world, local_rank):
     breakdown = {k: {"ms_per_step": v[0] / K, "share": v[0] / total_ms} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     peaks = load_peaks()
     alg_bytes = HEAD_FRAMES * (768 * 2 + 9 * 4)
+    # Tensor-core work the pipeline executes per frame (fp32-accurate products as three bf16 passes, hi*hi + lo*hi +
+    # hi*lo): bottleneck projections once per frame, lin0 on all 31 steps of the frame's window, the input gates on the
+    # 21 steps each direction runs, the recurrence (64 x 256 per step and direction).  The GEMM stages are bound by
+    # this, not by HBM: it also sets the floor of the whole head (total / sustained bf16 peak).
+    f_proj, f_lin0 = 2 * 3 * 768 * 384, 2 * 3 * 31 * 384 * 256
+    f_ih, f_rec = 2 * 3 * 42 * 256 * 256, 2 * 3 * 42 * 64 * 256
+    def _tf(tag, flop):
+        ms = breakdown.get(tag, {}).get("ms_per_step")
+        return None if not ms else {"tflops": HEAD_FRAMES * flop / (ms / 1000.0) / 1e12,
+                                    "frac_of_sustained": HEAD_FRAMES * flop / (ms / 1000.0) / 1e12 / peaks["tf_sustained"]}
+    tensor = {"flop_per_frame": f_proj + f_lin0 + f_ih + f_rec,
+              "floor_ms_per_1M_frames_at_sustained_peak": (f_proj + f_lin0 + f_ih + f_rec) * 1e6 / (peaks["tf_sustained"] * 1e12) * 1e3,
+              "head_lin0_gemm": _tf("head_lin0_gemm", f_lin0), "head_ih_gemm": _tf("head_ih_gemm", f_ih),
+              "head_proj_gemm": _tf("head_proj_gemm", f_proj)}
     cpu_baseline = gpu_eager = None
     if rank == 0 and world == 1 and not args.no_gpu_baseline:
         try:
@@ -284,7 +298,7 @@ def run_head(args, rank, world, local_rank):
                          "peak": peaks["hbm"], "unit": "GB/s", "frac": alg_bytes / (ms_max / K / 1000.0) / 1e9 / peaks["hbm"],
                          "traffic": None, "note": "algorithmic bytes = 1536 B in + 36 B out per frame; the pipeline is "
                                                   "bound by its intermediates and the recurrence, not by this traffic"},
-            "stages": breakdown, "cpu_baseline": cpu_baseline, "gpu_eager_baseline": gpu_eager,
+            "stages": breakdown, "tensor": tensor, "cpu_baseline": cpu_baseline, "gpu_eager_baseline": gpu_eager,
             "e2e": {"value": world * K * HEAD_FRAMES / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": HEAD_FRAMES * 768 * 2,
                     "d2h_bytes_per_step": HEAD_FRAMES * 9 * 4},
             "clocks": clocks, "gpu_launches": int(launches)}), flush=True)
