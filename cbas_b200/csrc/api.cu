@@ -51,6 +51,14 @@ ProfScope::~ProfScope() {
     if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].b, stream);
 }
 
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("CBAS_B200_PDL");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
 int sm_count() {
     static std::atomic<int> cache[64] = {};
     int dev = 0;

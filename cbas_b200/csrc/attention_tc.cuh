@@ -391,6 +391,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();     // the QKV GEMM's output is read from here on (the prologue above overlapped its tail)
+    pdl_trigger();
 
     if (warp == ATC_PRODUCER_WARP) {
         // -------------------------------------------------------------------- TMA producer (one elected lane issues)

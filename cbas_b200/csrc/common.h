@@ -16,6 +16,15 @@ int fail(const std::string& msg);               // set_error + return 1
 int check_cuda(cudaError_t e, const char* what);  // 0 if cudaSuccess, else records and returns 1
 void count_launch(int n = 1);
 int sm_count();  // of the calling thread's current device
+// Programmatic dependent launch for the kernels that call pdl_wait() (GEMM, attention, LayerNorm): off unless
+// CBAS_B200_PDL=1 (parity-green, but no measurable gain on the power-capped step: profiles/pdl_ab_r02.txt).  Fills `attr` and returns 1 when the launch should carry the attribute, else 0.
+bool pdl_enabled();
+inline int pdl_attr(cudaLaunchAttribute* attr) {
+    if (!pdl_enabled()) return 0;
+    attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr->val.programmaticStreamSerializationAllowed = 1;
+    return 1;
+}
 
 // Per-device "configured" state for cudaFuncSetAttribute(MaxDynamicSharedMemorySize), which is a per-DEVICE
 // attribute: one entry per device ordinal.  The value is published only after the attribute call has succeeded, so

@@ -60,14 +60,24 @@ int launch_layernorm(const float* in, long long in_row_stride, const float* g, c
     ProfScope prof(tag, s);
     const int threads = 256, rows_per_block = threads / 32;
     const int grid = (rows + rows_per_block - 1) / rows_per_block;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_attr(&attr[0]);  // the kernel waits for its predecessor itself (pdl_wait)
+    const int rev = t_reverse;
+    cudaError_t err;
     switch (D) {
-        case 384: layernorm_kernel<384, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps, t_reverse); break;
-        case 768: layernorm_kernel<768, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps, t_reverse); break;
-        case 1024: layernorm_kernel<1024, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps, t_reverse); break;
-        case 128: layernorm_kernel<128, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps, t_reverse); break;
-        case 256: layernorm_kernel<256, OutT><<<grid, threads, 0, s>>>(in, in_row_stride, g, b, out, rows, eps, t_reverse); break;
+        case 384: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<384, OutT>, in, in_row_stride, g, b, out, rows, eps, rev); break;
+        case 768: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<768, OutT>, in, in_row_stride, g, b, out, rows, eps, rev); break;
+        case 1024: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<1024, OutT>, in, in_row_stride, g, b, out, rows, eps, rev); break;
+        case 128: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<128, OutT>, in, in_row_stride, g, b, out, rows, eps, rev); break;
+        case 256: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<256, OutT>, in, in_row_stride, g, b, out, rows, eps, rev); break;
         default: return fail("LayerNorm width " + std::to_string(D) + " not instantiated (384/768/1024)");
     }
+    if (err != cudaSuccess) return check_cuda(err, "layernorm_kernel launch");
     count_launch();
     return check_cuda(cudaGetLastError(), "layernorm_kernel launch");
 }
@@ -142,8 +152,17 @@ int launch_attention_tc_tk(const CUtensorMap& tq, const CUtensorMap& tkv, const 
                            const AttnTcParams& p, int smem, int grid, cudaStream_t s) {
     static DeviceSmemOptIn optin;
     CBAS_CHECK(optin.ensure(attention_tc_kernel<TK>, smem));
-    attention_tc_kernel<TK><<<grid, ATC_THREADS, smem, s>>>(tq, tkv, to, to1, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(ATC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_attr(&attr[0]);  // the kernel waits for the QKV GEMM itself (pdl_wait after its prologue)
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, attention_tc_kernel<TK>, tq, tkv, to, to1, p);
     count_launch();
+    if (err != cudaSuccess) return check_cuda(err, "attention_tc_kernel launch");
     return check_cuda(cudaGetLastError(), "attention_tc_kernel launch");
 }
 

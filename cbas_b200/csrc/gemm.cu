@@ -80,13 +80,13 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 1 + pdl_attr(&attr[1]);
     cudaError_t err = cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, p);
     count_launch();
     if (err != cudaSuccess) return check_cuda(err, "gemm_tcgen05_kernel launch");

@@ -215,6 +215,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // everything above overlapped the previous kernel's tail (programmatic dependent launch); its results are needed
+    // from here on.  The next kernel in the stream may start its own prologue as SMs free up.
+    pdl_wait();
+    pdl_trigger();
 
     if (warp == kProducerWarp) {
         // ---------------------------------------------------------------- TMA producer (whole warp, one elected lane)

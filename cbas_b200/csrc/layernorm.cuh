@@ -17,6 +17,8 @@ layernorm_kernel(const float* __restrict__ in, long long in_row_stride, const fl
     constexpr int V = D / 128;  // float4 per lane
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();  // programmatic dependent launch: the residual stream is complete from here on
     if (warp >= rows) return;
     if (reverse) warp = rows - 1 - warp;  // last rows first: the ones the preceding kernel left in L2
     const float4* src = reinterpret_cast<const float4*>(in + (long long)warp * in_row_stride * D);
