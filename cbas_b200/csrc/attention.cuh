@@ -45,8 +45,9 @@ __device__ __forceinline__ void rope_pair(uint4& lo, uint4& hi, const float* __r
     }
 }
 
-// One key block: NT n-tiles of 8 keys starting at key0.
-template <int NT>
+// One key block: NT n-tiles of 8 keys starting at key0.  VF16: V (and therefore P) as IEEE f16 - the layout the
+// tcgen05 kernels' QKV epilogue leaves (attention_tc_split.cuh runs a frame's few leftover query rows through here).
+template <int NT, bool VF16 = false>
 __device__ __forceinline__ void att_key_block(const uint32_t (&qf)[4][4], uint32_t sK, uint32_t sV, int key0, int T,
                                               float scale_log2, float (&o)[8][4], float (&m)[2], float (&l)[2],
                                               int lane) {
@@ -107,18 +108,30 @@ __device__ __forceinline__ void att_key_block(const uint32_t (&qf)[4][4], uint32
 #pragma unroll
     for (int kk = 0; kk < NT / 2; ++kk) {
         uint32_t pa[4];
-        pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-        pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-        pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-        pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        if constexpr (VF16) {
+            pa[0] = pack_f16(s[2 * kk][0], s[2 * kk][1]);
+            pa[1] = pack_f16(s[2 * kk][2], s[2 * kk][3]);
+            pa[2] = pack_f16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+            pa[3] = pack_f16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        } else {
+            pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+            pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+            pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+            pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        }
 #pragma unroll
         for (int d = 0; d < 8; d += 2) {
             uint32_t b0, b1, b2, b3;
             const int key = key0 + kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
             const int chunk = d + (lane >> 4);
             ldmatrix_x4_trans(b0, b1, b2, b3, sV + att_swz(key, chunk));
-            mma_bf16_16816(o[d], pa, b0, b1);
-            mma_bf16_16816(o[d + 1], pa, b2, b3);
+            if constexpr (VF16) {
+                mma_f16_16816(o[d], pa, b0, b1);
+                mma_f16_16816(o[d + 1], pa, b2, b3);
+            } else {
+                mma_bf16_16816(o[d], pa, b0, b1);
+                mma_bf16_16816(o[d + 1], pa, b2, b3);
+            }
         }
     }
 }

@@ -13,7 +13,14 @@
 //     is no running rescale of O inside the loop.  Pipeline 1 runs half a tile behind pipeline 0 and ITS warps do
 //     the merge, staging and store; pipeline 0 never waits for pipeline 1 (its O_0 simply stays in TMEM until the
 //     merge has read it), so one pipeline's MMAs and drain fall into the other's softmax;
-//   * the query tiles of a frame (three of them) run one after the other against the resident K and V.
+//   * the query tiles of a frame run one after the other against the resident K and V;
+//   * LEFTOVER ROWS: when the last query tile holds at most 16 real rows (256-px frames with 16-px patches: 261 tokens
+//     = 2 x 128 + 5) it does not go through the tensor-core pipeline at all - a full tile pass (S MMA, two softmax
+//     passes, exchange, P V, merge) for five rows cost a third of the item.  The rotation warps, idle once Q and K
+//     are rotated, run those rows through the warp-level mma.sync flash routine of attention.cuh (att_key_block: same
+//     swizzled shared-memory rows, fp32 online softmax, f16 P and V) while the two full tiles are on tcgen05, and
+//     stores them straight to global memory (the key blocks are dealt to the four rotation warps and their partial
+//     (m, l, O) merged lane by lane through shared memory).  Q / K / V are handed back to the TMA producer only when it is done too.
 //
 // Shared memory holds ONE frame-head at a time (Q tiles + K + V, up to 134 KB) next to the output staging rows and
 // the RoPE table, so the next item's loads start when the last S / PV MMAs of the current one retire; that bubble
@@ -21,17 +28,20 @@
 // Reference semantics: HF modeling_dinov3_vit.py:316-329 / modeling_dinov2_with_registers.py eager_attention_forward
 // (scale 1/8, no mask, non-causal).
 #pragma once
+#include "attention.cuh"
 #include "attention_tc.cuh"
 
 namespace cbas {
 
+constexpr int ATS_LEFT_BYTES = ATC_ROT_WARPS * 36 * 32 * 4;  // leftover rows: per rotation warp [36 values][32 lanes] fp32
 constexpr int ATS_XCHG_BYTES = (2 * 2 * 128 + 2 * 2 * 2 * 128 + 2 * 2 * 128) * 4;  // max [pipe][half][row]; per tile parity: sums [pipe][half][row], block max [pipe][row]
 
 __host__ __device__ inline int ats_key_block0(int TK) { return ((TK + 31) / 32) * 16; }
 __host__ __device__ inline int ats_smem_bytes(int TK, int T, int prefix, bool rope) {
     const int nq = (T + 127) / 128;
+    const bool leftover = T - 128 * (nq - 1) <= 16;  // the last query tile's rows go through the rotation warps
     return nq * 16384 + 2 * TK * 128 + atc_stage_bytes(T) + (rope ? atc_rope_bytes(T, prefix) : 0) + ATS_XCHG_BYTES + 1024 +
-           256;
+           256 + (leftover ? ATS_LEFT_BYTES : 0);
 }
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
@@ -47,6 +57,9 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
     const int nq = (T + 127) >> 7;
     const int TK0 = ats_key_block0(TK), TK1 = TK - TK0;
     const bool rope = p.rope_cos != nullptr;
+    const int left_rows = T - 128 * (nq - 1);          // real rows of the last query tile
+    const bool leftover = left_rows <= 16;              // ... few enough for one mma.sync m16 tile on a rotation warp
+    const int nq_tc = leftover ? nq - 1 : nq;           // query tiles that go through the tcgen05 pipelines
     uint8_t* q_s = smem;                          // nq tiles of [128][128 B]
     uint8_t* k_s = smem + nq * 16384;             // [TK][128 B]
     uint8_t* v_s = k_s + TK * 128;                // [TK][128 B]
@@ -54,6 +67,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
     __half2* rope_tab = reinterpret_cast<__half2*>(ostage + atc_stage_bytes(T));
     float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(rope_tab) + (rope ? atc_rope_bytes(T, p.prefix) : 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + ATS_XCHG_BYTES);
+    float* left_x = reinterpret_cast<float*>(bars + 32);  // [rotation warp][36][32], present in leftover mode only
     uint64_t* qk_full = bars;        // TMA -> rotation warps (or MMA): Q tiles + K landed
     uint64_t* qk_empty = bars + 1;   // both MMA warps -> TMA: the item's last S MMAs retired
     uint64_t* v_full = bars + 2;     // TMA -> MMA
@@ -77,9 +91,9 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
     }
     if (warp == ATC_MMA_WARP0 && lane == 0) {
         mbar_init(qk_full, 1);
-        mbar_init(qk_empty, 2);
+        mbar_init(qk_empty, leftover ? 3 : 2);  // both MMA warps (+ the leftover-rows warp)
         mbar_init(v_full, 1);
-        mbar_init(v_empty, 2);
+        mbar_init(v_empty, leftover ? 3 : 2);
         mbar_init(qk_ready, ATC_ROT_WARPS);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1);
@@ -141,7 +155,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
         int it = 0, g = 0;
         for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
             mbar_wait(rope ? qk_ready : qk_full, it & 1);
-            for (int qt = 0; qt < nq; ++qt, ++g) {
+            for (int qt = 0; qt < nq_tc; ++qt, ++g) {
                 // S overwrites the previous tile's P (same columns): that tile's PV must have retired.  O sits at
                 // +192..+256, beyond any S of this kernel (TKp <= 192), so S does not wait for the merge.
                 if (g > 0) mbar_wait(&o_full[pp], (g - 1) & 1);
@@ -151,7 +165,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_bf16_ss(t_pipe, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
                     umma_commit(&s_full[pp]);
-                    if (qt == nq - 1) umma_commit(qk_empty);
+                    if (qt == nq_tc - 1) umma_commit(qk_empty);
                 }
                 __syncwarp();
                 if (qt == 0) mbar_wait(v_full, it & 1);
@@ -167,29 +181,106 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
                         }
                     }
                     umma_commit(&o_full[pp]);
-                    if (qt == nq - 1) umma_commit(v_empty);
+                    if (qt == nq_tc - 1) umma_commit(v_empty);
                 }
                 __syncwarp();
             }
         }
     } else if (warp >= ATC_ROT_WARP0) {
-        // ------------------------------------------------------------------- RoPE rotation warps
-        if (rope) {
+        // ------------------------------------------------------------------- RoPE rotation warps (+ leftover rows)
+        if (rope || leftover) {
             const int rtid = threadIdx.x - ATC_ROT_WARP0 * 32;
             const int nrot = T - p.prefix;
             const int units = 2 * nrot * 4;
             int it = 0;
             for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
                 mbar_wait(qk_full, it & 1);
-                for (int u = rtid; u < units; u += ATC_ROT_WARPS * 32) {
-                    const int ridx = u >> 2, cpair = u & 3;
-                    const int isk = ridx >= nrot;
-                    const int tok = p.prefix + ridx - (isk ? nrot : 0);
-                    atc_rope_unit(isk ? k_s : q_s, tok, cpair, rope_tab + (tok - p.prefix) * 32);
+                if (rope) {
+                    for (int u = rtid; u < units; u += ATC_ROT_WARPS * 32) {
+                        const int ridx = u >> 2, cpair = u & 3;
+                        const int isk = ridx >= nrot;
+                        const int tok = p.prefix + ridx - (isk ? nrot : 0);
+                        atc_rope_unit(isk ? k_s : q_s, tok, cpair, rope_tab + (tok - p.prefix) * 32);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(qk_ready);
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(qk_ready);
+                if (leftover) {
+                    // the last query tile's few rows: one m16 tile against all keys.  The 16-key blocks are dealt to the
+                    // four rotation warps (flash-style online softmax inside a warp), the partial (m, l, O) - identical
+                    // fragment layout in every warp, so the merge is lane by lane - meet in shared memory.
+                    if (rope) mbar_wait(qk_ready, it & 1);  // every rotation warp has finished its share of Q and K
+                    mbar_wait(v_full, it & 1);
+                    const int rw = warp - ATC_ROT_WARP0;
+                    const uint32_t sQ = smem_u32(q_s) + (nq - 1) * 16384, sK = smem_u32(k_s), sV = smem_u32(v_s);
+                    uint32_t qf[4][4];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int row = (lane & 7) + (((lane >> 3) & 1) << 3);
+                        const int chunk = 2 * kk + (lane >> 4);
+                        ldmatrix_x4(qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], sQ + att_swz(row, chunk));
+                    }
+                    float o[8][4];
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
+                    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+                    const int nb = TK >> 4;
+                    for (int b = rw * nb / ATC_ROT_WARPS; b < (rw + 1) * nb / ATC_ROT_WARPS; ++b)
+                        att_key_block<2, true>(qf, sK, sV, b * 16, T, p.scale_log2, o, m, l, lane);
+                    float* mine = left_x + rw * 36 * 32 + lane;
+                    if (rw != 0) {
+#pragma unroll
+                        for (int d = 0; d < 8; ++d)
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) mine[(4 * d + e) * 32] = o[d][e];
+                        mine[32 * 32] = m[0]; mine[33 * 32] = m[1]; mine[34 * 32] = l[0]; mine[35 * 32] = l[1];
+                    }
+                    named_bar_sync(10, 32 * ATC_ROT_WARPS);  // partial results written; nobody reads Q / K / V any more
+                    if (rw == 0) {
+#pragma unroll 1
+                        for (int ow = 1; ow < ATC_ROT_WARPS; ++ow) {
+                            const float* other = left_x + ow * 36 * 32 + lane;
+                            float sc_mine[2], sc_other[2];
+#pragma unroll
+                            for (int r = 0; r < 2; ++r) {
+                                const float mo = other[(32 + r) * 32];
+                                const float mn = fmaxf(m[r], mo);
+                                sc_mine[r] = m[r] == -INFINITY ? 0.f : ex2_approx(m[r] - mn);
+                                sc_other[r] = mo == -INFINITY ? 0.f : ex2_approx(mo - mn);
+                                m[r] = mn;
+                                l[r] = l[r] * sc_mine[r] + other[(34 + r) * 32] * sc_other[r];
+                            }
+#pragma unroll
+                            for (int d = 0; d < 8; ++d)
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    o[d][e] = o[d][e] * sc_mine[e >> 1] + other[(4 * d + e) * 32] * sc_other[e >> 1];
+                        }
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+                            l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+                            l[r] = 1.0f / l[r];
+                        }
+                        const int f = w / p.heads, h = w % p.heads;
+                        const int r0 = lane >> 2, r1 = r0 + 8;
+                        __nv_bfloat16* ob = p.out + ((long long)f * T + 128 * (nq - 1)) * p.D + h * 64 + 2 * (lane & 3);
+#pragma unroll
+                        for (int d = 0; d < 8; ++d) {
+                            if (r0 < left_rows)
+                                *reinterpret_cast<uint32_t*>(ob + (long long)r0 * p.D + d * 8) = pack_bf16(o[d][0] * l[0], o[d][1] * l[0]);
+                            if (r1 < left_rows)
+                                *reinterpret_cast<uint32_t*>(ob + (long long)r1 * p.D + d * 8) = pack_bf16(o[d][2] * l[1], o[d][3] * l[1]);
+                        }
+                        // Q, K and V of this item are no longer read by the rotation warps
+                        if (lane == 0) {
+                            mbar_arrive(qk_empty);
+                            mbar_arrive(v_empty);
+                        }
+                    }
+                    named_bar_sync(11, 32 * ATC_ROT_WARPS);  // the scratch rows may be rewritten
+                }
             }
         }
     } else {
@@ -212,7 +303,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
         int it = 0, g = 0;
         for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++it) {
             const int f = w / p.heads, h = w % p.heads;
-            for (int qt = 0; qt < nq; ++qt, ++g) {
+            for (int qt = 0; qt < nq_tc; ++qt, ++g) {
                 const int row = qt * 128 + rit;
                 const bool warp_has_rows = (qt * 128 + quarter * 32) < T;
                 float* sums = sums_all + (g & 1) * 512;

@@ -145,9 +145,11 @@ def test_context_invariance_at_full_size():
     probs = head.infer_embeddings(emb)
     assert torch.isfinite(probs).all()
     assert (probs.sum(1) - 1).abs().max() < 1e-5
-    a, b = 500_000, 500_400
-    sub = head.infer_embeddings(emb[a - 15:b + 15].contiguous())
-    assert (sub[15:-15] - probs[a:b]).abs().max() < 1e-6
+    # one range inside a chunk of the window stages, one across a chunk boundary (chunks of 2 * 148 * 128 = 37 888 windows:
+    # different chunks, different 128-window tiles of the recurrence kernel, same numbers)
+    for a, b in ((500_000, 500_400), (3 * 37_888 - 200, 3 * 37_888 + 200)):
+        sub = head.infer_embeddings(emb[a - 15:b + 15].contiguous())
+        assert (sub[15:-15] - probs[a:b]).abs().max() < 1e-6
 
 
 def test_actogram_fixture_from_reference(golden_dir):
