@@ -48,10 +48,10 @@ int make_tmap(CUtensorMap* map, const void* base, bool f32, int rows, int cols, 
     return 0;
 }
 
-template <int BLOCK_N, int EPI, int CG>
+template <int BLOCK_N, int EPI, int CG, bool LNC = false>
 int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-    using Cfg = GemmCfg<BLOCK_N, CG, gemm_epi_double_stage(EPI), gemm_epi_ln_producer(EPI) ? gemm_ln_bufs(EPI) : 0>;
-    auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI, CG>;
+    using Cfg = GemmCfg<BLOCK_N, CG, gemm_epi_double_stage(EPI), gemm_epi_ln_producer(EPI) ? gemm_ln_bufs(EPI) : 0, LNC>;
+    auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI, CG, LNC>;
     // the opt-in is a per-DEVICE attribute: one flag per instantiation and device ordinal
     static DeviceSmemOptIn optin;
     CBAS_CHECK(optin.ensure(kern, Cfg::kSmemBytes));
@@ -100,13 +100,20 @@ int launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
     if (int rc = make_tmap(&ta, A, false, p.M, p.a_wrap ? p.a_wrap : p.K, lda, GEMM_BLOCK_K, GEMM_BLOCK_M)) return rc;
     if (int rc = make_tmap(&tb, W, false, p.N, p.K, ldw, GEMM_BLOCK_K, BLOCK_N / CG)) return rc;
     switch (epi) {
-        case EPI_BIAS_BF16: return launch_one<BLOCK_N, EPI_BIAS_BF16, CG>(ta, tb, p, stream);
-        case EPI_BIAS_GELU_BF16: return launch_one<BLOCK_N, EPI_BIAS_GELU_BF16, CG>(ta, tb, p, stream);
+        // bf16-output epilogues: p.ln_in selects the fused-LayerNorm consumer instantiation (its own shared-memory plan)
+        case EPI_BIAS_BF16:
+            if (p.ln_in) return launch_one<BLOCK_N, EPI_BIAS_BF16, CG, true>(ta, tb, p, stream);
+            return launch_one<BLOCK_N, EPI_BIAS_BF16, CG>(ta, tb, p, stream);
+        case EPI_BIAS_GELU_BF16:
+            if (p.ln_in) return launch_one<BLOCK_N, EPI_BIAS_GELU_BF16, CG, true>(ta, tb, p, stream);
+            return launch_one<BLOCK_N, EPI_BIAS_GELU_BF16, CG>(ta, tb, p, stream);
         case EPI_RESID_F32: return launch_one<BLOCK_N, EPI_RESID_F32, CG>(ta, tb, p, stream);
         case EPI_PATCH_F32: return launch_one<BLOCK_N, EPI_PATCH_F32, CG>(ta, tb, p, stream);
         case EPI_BIAS_F32: return launch_one<BLOCK_N, EPI_BIAS_F32, CG>(ta, tb, p, stream);
         case EPI_BIAS_GELU_F32: return launch_one<BLOCK_N, EPI_BIAS_GELU_F32, CG>(ta, tb, p, stream);
-        case EPI_BIAS_BF16_VF16: return launch_one<BLOCK_N, EPI_BIAS_BF16_VF16, CG>(ta, tb, p, stream);
+        case EPI_BIAS_BF16_VF16:
+            if (p.ln_in) return launch_one<BLOCK_N, EPI_BIAS_BF16_VF16, CG, true>(ta, tb, p, stream);
+            return launch_one<BLOCK_N, EPI_BIAS_BF16_VF16, CG>(ta, tb, p, stream);
         // long mainloop: one old-h slab buffer per epilogue group and a deeper operand ring; short: prefetched slabs
         case EPI_RESID_LN_F32:
         case EPI_RESID_LN1_F32:

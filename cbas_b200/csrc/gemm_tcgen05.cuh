@@ -42,11 +42,6 @@
 #pragma once
 #include "ptx.cuh"
 
-#ifdef LN_CONS_NO_C1
-#define LN_C1_LOAD(ptr) make_float4(0.f, 0.f, 0.f, 0.f)
-#else
-#define LN_C1_LOAD(ptr) __ldg(reinterpret_cast<const float4*>(ptr))
-#endif
 
 namespace cbas {
 
@@ -121,14 +116,18 @@ __host__ __device__ constexpr int gemm_ln_bufs(int epi) { return epi == EPI_RESI
 // L2 -> shared-memory operand traffic per FLOP by a third - the 1-CTA mainloop is bound by exactly that traffic.
 // kDoubleStage: two staging slabs per epilogue group (the bulk store of slab s overlaps the math of slab s+1) at
 // the price of one mainloop stage - worth it only for the ALU-heavy GELU epilogues.
-template <int BLOCK_N, int CG = 1, bool kDoubleStage = false, int kLnBufs = 0>
+template <int BLOCK_N, int CG = 1, bool kDoubleStage = false, int kLnBufs = 0, bool kLnConsumer = false>
 struct GemmCfg {
     static constexpr int kStageA = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;  // 16 KB
     static constexpr int kStageB = (BLOCK_N / CG) * GEMM_BLOCK_K * 2;
     static constexpr int kStage = kStageA + kStageB;
     static constexpr int kSlabsPerGroup = kDoubleStage ? 2 : 1;
     static constexpr int kStaging = 2 * (kLnBufs ? kLnBufs : kSlabsPerGroup) * GEMM_SLAB_BYTES;
-    static constexpr int kSide = 1024;  // per-row LayerNorm scale / offset of the current tile (consumer epilogues)
+    // LayerNorm consumers: per-row scale / offset of the current tile [128] float2, then the per-column constants
+    // c1 | c2 of the current and the next tile, [2][2][BLOCK_N] floats (written by the helper warp, read by every
+    // epilogue thread as shared-memory broadcasts: as global loads they were the epilogue's longest stall, the ~28 KB
+    // of L1 left next to 227 KB of shared memory does not keep them)
+    static constexpr int kSide = kLnConsumer ? 1024 + 2 * 2 * BLOCK_N * 4 : 1024;
     static constexpr int kBudget = 232448 - 1024 - 256 - kSide - kStaging;
 #ifdef GEMM_FORCE_STAGES  // A/B builds only (tools/build_ref_lib.py WORKTREE -DGEMM_FORCE_STAGES=4)
     static constexpr int kStages = kBudget / kStage > GEMM_FORCE_STAGES ? GEMM_FORCE_STAGES : kBudget / kStage;
@@ -141,13 +140,15 @@ struct GemmCfg {
     static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
-template <int BLOCK_N, int EPI, int CG>
+template <int BLOCK_N, int EPI, int CG, bool LNC = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
     constexpr bool kLnProducer = gemm_epi_ln_producer(EPI);
     constexpr int kLnBufs = kLnProducer ? gemm_ln_bufs(EPI) : 0;
-    using Cfg = GemmCfg<BLOCK_N, CG, gemm_epi_double_stage(EPI), kLnBufs>;
+    constexpr bool kLnConsumer = LNC;  // fused LayerNorm, consumer side (bf16-output epilogues, p.ln_in set)
+    static_assert(!LNC || gemm_epi_out_bf16(EPI), "LayerNorm-consumer epilogues write bf16");
+    using Cfg = GemmCfg<BLOCK_N, CG, gemm_epi_double_stage(EPI), kLnBufs, kLnConsumer>;
     static_assert(CG == 1 || CG == 2, "cta_group");
     static_assert((BLOCK_N / CG) % 8 == 0 && BLOCK_N % 16 == 0, "UMMA N");
     constexpr int kStages = Cfg::kStages;
@@ -165,6 +166,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint8_t* smem_b = smem + kStages * Cfg::kStageA;
     uint8_t* smem_stage = smem + kStages * Cfg::kStage;  // 4 x 16 KB, 1024-aligned
     float2* rowc = reinterpret_cast<float2*>(smem_stage + Cfg::kStaging);  // [128] {rstd, -mean * rstd} (LN consumer)
+    float* colc = reinterpret_cast<float*>(smem_stage + Cfg::kStaging + 1024);  // [2 tile parity][c1 | c2][BLOCK_N] (LN consumer)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + Cfg::kStaging + Cfg::kSide);
     uint64_t* full_bar = bars;                      // [kStages] TMA -> MMA
     uint64_t* empty_bar = bars + kStages;           // [kStages] MMA -> TMA
@@ -288,17 +290,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp == GEMM_EPI_WARPS + 3) {
         // ---------------------------------------------------------------- LayerNorm helper (consumer and producer)
-        if constexpr (kOutBf16 || kLnProducer) {
-            if (p.ln_in) {
+        if constexpr (kLnConsumer || kLnProducer) {
+            {
                 int iter = 0;
                 for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++iter) {
                     const int m_blk = p.reverse ? m_blocks - 1 - tile / n_blocks : tile / n_blocks, n_blk = tile % n_blocks;
                     const int m_base = (m_blk * CG + (int)cta_rank) * GEMM_BLOCK_M;
                     // this tile's per-column constants (BLOCK_N floats each): first touch by this warp, L1 hits for the
                     // epilogue warps
-                    if (lane * 32 < BLOCK_N) {
+                    float4 cc[kLnConsumer ? BLOCK_N / 64 : 1];  // this lane's share of c1 | c2: 2 * BLOCK_N floats over 32 lanes
+                    if constexpr (kLnConsumer) {
+#pragma unroll
+                        for (int i = 0; i < BLOCK_N / 64; ++i) {
+                            const int idx = (i * 32 + lane) * 4;  // 0 .. 2 * BLOCK_N
+                            const float* src = idx < BLOCK_N ? p.ln_c1 + n_blk * BLOCK_N + idx
+                                                             : p.bias + n_blk * BLOCK_N + (idx - BLOCK_N);
+                            cc[i] = __ldg(reinterpret_cast<const float4*>(src));
+                        }
+                    } else if (lane * 32 < BLOCK_N) {
                         if (p.bias) prefetch_l1(p.bias + n_blk * BLOCK_N + lane * 32);
-                        if (!kLnProducer) prefetch_l1(p.ln_c1 + n_blk * BLOCK_N + lane * 32);
                     }
                     float2 rc[GEMM_BLOCK_M / 32];
 #pragma unroll
@@ -331,6 +341,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     mbar_wait(rowc_empty, (iter & 1) ^ 1);  // the epilogue has taken the previous tile's values
 #pragma unroll
                     for (int r = 0; r < GEMM_BLOCK_M / 32; ++r) rowc[r * 32 + lane] = rc[r];
+                    if constexpr (kLnConsumer) {
+                        // every epilogue warp has started tile iter - 1, so none is still reading tile iter - 2's constants
+                        float4* dst = reinterpret_cast<float4*>(colc + (iter & 1) * 2 * BLOCK_N);
+#pragma unroll
+                        for (int i = 0; i < BLOCK_N / 64; ++i) dst[i * 32 + lane] = cc[i];
+                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(rowc_full);
                 }
@@ -471,8 +487,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
             // fused LayerNorm, consumer side: this row's rstd and -mean * rstd, prepared by the helper warp
             float ln_alpha = 1.f, ln_ndelta = 0.f;
-            if constexpr (kOutBf16) {
-                if (p.ln_in) {
+            if constexpr (kLnConsumer) {
+                {
                     mbar_wait(rowc_full, iter & 1);
                     const float2 rc = rowc[row_in_tile];
                     ln_alpha = rc.x; ln_ndelta = rc.y;
@@ -511,23 +527,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             if (CG == 1) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_cluster(&tmem_empty[acc], 0);
                         }
                     }
-                    if (kOutBf16 && p.ln_in) {
-                        // LN(h) W^T + b = rstd * acc - rstd * mean * c1 + c2   (bias holds c2)
+                    if constexpr (kLnConsumer) {
+                        // LN(h) W^T + b = rstd * acc - rstd * mean * c1 + c2   (bias holds c2); c1 | c2 from shared memory
+                        const float* cc1 = colc + (iter & 1) * 2 * BLOCK_N + c0;
 #pragma unroll
                         for (int j = 0; j < kHalf; j += 4) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                            const float4 c = LN_C1_LOAD(p.ln_c1 + n0 + j);
-#ifdef LN_CONS_NO_C1  // timing experiment only (wrong result): what the epilogue costs without the c1 term
-                            x[j] = fmaf(ln_alpha, x[j], b.x + c.x * 0.f);
-                            x[j + 1] = fmaf(ln_alpha, x[j + 1], b.y);
-                            x[j + 2] = fmaf(ln_alpha, x[j + 2], b.z);
-                            x[j + 3] = fmaf(ln_alpha, x[j + 3], b.w);
-#else
+                            const float4 b = *reinterpret_cast<const float4*>(cc1 + BLOCK_N + j);
+                            const float4 c = *reinterpret_cast<const float4*>(cc1 + j);
                             x[j] = fmaf(ln_alpha, x[j], fmaf(ln_ndelta, c.x, b.x));
                             x[j + 1] = fmaf(ln_alpha, x[j + 1], fmaf(ln_ndelta, c.y, b.y));
                             x[j + 2] = fmaf(ln_alpha, x[j + 2], fmaf(ln_ndelta, c.z, b.z));
                             x[j + 3] = fmaf(ln_alpha, x[j + 3], fmaf(ln_ndelta, c.w, b.w));
-#endif
                         }
                     } else if (p.bias) {
 #pragma unroll
