@@ -3,7 +3,8 @@
 // softmax(logits / max(1e-3, T))), plus the actogram binning of cbas.py:969-999.
 //
 // The reference builds every window on the host ([512,31,768] fp32 per batch, each embedding row shipped 31x)
-// and runs ~40 small launches per batch.  Here the per-frame work is hoisted out of the windows:
+// and runs ~40 small launches per batch.  Here the per-frame work is hoisted out of the windows and the window stages
+// run over chunks of up to 37 888 windows (two waves of 128-window tiles on 148 SMs; 7 launches per chunk):
 //
 //   H1 head_split_embed   f16 embeddings -> exact bf16 hi/lo split [n, 2F]; per-frame lin1 logits q = W1 x (fp32)
 //   H2 tcgen05 GEMM       P[n,384] = x (Wc|Wd|Wa)^T   - EMA, deltas and lin1 are linear, so the three 768->128
@@ -13,11 +14,13 @@
 //                         LayerNorm(128) x3 -> a_t[384] as bf16 hi/lo; linear branch = mean_t EMA(q) + b1
 //   H4 tcgen05 GEMM       Z = GELU(a W0^T + b0)                      [rows, 256] fp32
 //   H5 head_center_split  z - mean_t z  -> bf16 hi/lo
-//   H6 tcgen05 GEMM       G = z (Wih_f | Wih_r)^T + (b_ih + b_hh)    [rows, 512] fp32  (input half of the gates)
-//   H7 head_lstm_tc       the recurrence (lstm_hidden_size 64): persistent tcgen05 kernel, 128 windows per CTA, W_hh
-//                         (bf16 hi / lo) resident in shared memory, h fed back through shared memory, c in registers,
-//                         gates in TMEM (head_lstm_tc.cuh); only the steps that can reach the centre frames are run
-//                         (21 of 31 per direction).  lstm_hidden_size 128: head_lstm_dir, fp32 FMA, 4 windows per
+//   H6 tcgen05 GEMMs      G_dir = z Wih_dir^T + (b_ih + b_hh), one GEMM per direction over the steps that direction
+//                         runs.  Rows of the window stages are ordered t-MAJOR (row = t * windows + window), so the
+//                         forward direction's steps t < r and the reverse direction's t >= l (21 of 31 each for the
+//                         default head) are contiguous row ranges: [steps * windows, 256] fp32 per direction
+//   H7 head_lstm_tc       the recurrence (lstm_hidden_size 64): persistent tcgen05 kernel, one CTA per SM and
+//                         direction, two 128-window tiles in flight, W_hh (bf16 hi / lo) resident in shared memory, G
+//                         by TMA, h fed back through shared memory, c in registers, gates in TMEM (head_lstm_tc.cuh).  lstm_hidden_size 128: head_lstm_dir, fp32 FMA, 4 windows per
 //                         warp, the 256 KB W_hh streamed through L1/L2.
 //                         lstm_layers = 2: layer 0 runs all steps, its [fwd|rev] outputs are split to bf16 hi/lo
 //                         and go through one more input-gate GEMM (H6') and recurrence (H7').
