@@ -55,7 +55,7 @@ thread_local int t_reverse = 0;
 
 template <typename OutT>
 int launch_layernorm(const float* in, long long in_row_stride, const float* g, const float* b, OutT* out, int rows,
-                     int D, float eps, cudaStream_t s, int tag = PROF_LAYERNORM) {
+                     int D, float eps, cudaStream_t s, int tag = PROF_LAYERNORM, float* stats = nullptr) {
     if (rows <= 0) return 0;
     ProfScope prof(tag, s);
     const int threads = 256, rows_per_block = threads / 32;
@@ -70,11 +70,11 @@ int launch_layernorm(const float* in, long long in_row_stride, const float* g, c
     const int rev = t_reverse;
     cudaError_t err;
     switch (D) {
-        case 384: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<384, OutT>, in, in_row_stride, g, b, out, rows, eps, rev); break;
-        case 768: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<768, OutT>, in, in_row_stride, g, b, out, rows, eps, rev); break;
-        case 1024: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<1024, OutT>, in, in_row_stride, g, b, out, rows, eps, rev); break;
-        case 128: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<128, OutT>, in, in_row_stride, g, b, out, rows, eps, rev); break;
-        case 256: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<256, OutT>, in, in_row_stride, g, b, out, rows, eps, rev); break;
+        case 384: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<384, OutT>, in, in_row_stride, g, b, out, rows, eps, rev, stats); break;
+        case 768: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<768, OutT>, in, in_row_stride, g, b, out, rows, eps, rev, stats); break;
+        case 1024: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<1024, OutT>, in, in_row_stride, g, b, out, rows, eps, rev, stats); break;
+        case 128: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<128, OutT>, in, in_row_stride, g, b, out, rows, eps, rev, stats); break;
+        case 256: err = cudaLaunchKernelEx(&cfg, layernorm_kernel<256, OutT>, in, in_row_stride, g, b, out, rows, eps, rev, stats); break;
         default: return fail("LayerNorm width " + std::to_string(D) + " not instantiated (384/768/1024)");
     }
     if (err != cudaSuccess) return check_cuda(err, "layernorm_kernel launch");
@@ -295,7 +295,8 @@ struct cbas_encoder {
     bool prune_last_layer = true;      // false: run the last block on every token
     int attention_impl = 0;            // 0 auto, 1 mma.sync, 2 tcgen05
     int resize_tiled = 2;              // 0 per-pixel kernel, 1 general tiled kernel, 2 column-per-thread kernel
-    int ln_fused = CBAS_LN_FUSED_DEFAULT;  // 1: norm1 / norm2 inside the GEMM epilogues, 0: standalone LayerNorm kernels
+    int ln_fused = CBAS_LN_FUSED_DEFAULT;  // 0: standalone LayerNorm kernels, 1: norm1 / norm2 inside the GEMM epilogues,
+                                           // 2: norm1 fused (down GEMM -> next block's QKV GEMM), norm2 standalone
     bool serpentine = true;            // standalone-LayerNorm path: consecutive kernels walk the rows in opposite directions
     int direction = 0;                 //   ... direction of the last kernel launched by the previous block
     float* ones = nullptr;             // [D] ones / zeros: unit gamma and zero beta for the standalone LayerNorm path
@@ -503,8 +504,44 @@ int encoder_layer_unfused(cbas_encoder* e, int li, int n, cudaStream_t s, bool c
     return launch_gemm(e->u, I, (const __nv_bfloat16*)L.w_down, I, p, EPI_RESID_F32, s, PROF_DOWN_GEMM);
 }
 
+// Hybrid (CBAS_OPT_LN_FUSION 2): only norm1 is fused.  The down GEMM is long enough (K = 4 D) to hide the producer
+// epilogue and the QKV GEMM's consumer epilogue costs ~7 %, together less than half of the LayerNorm pass they replace;
+// the short-K proj GEMM (HBM-bound, +57 % as a producer) and the GELU epilogue of the up GEMM (already the busiest part
+// of that kernel) are left alone: proj reduces into h as in the standalone path and norm2 stays a kernel, which also
+// writes the statistics row (shift = the row's exact mean) the down producer starts from.
+int encoder_layer_hybrid(cbas_encoder* e, int li, int n, cudaStream_t s) {
+    const cbas_encoder_cfg& c = e->cfg;
+    const cbas_layer_weights& L = e->layers[li];
+    const int D = c.hidden, I = c.intermediate, T = e->T, M = n * T;
+    const bool tc = use_attention_tc(e->attention_impl, T, c.prefix_tokens, e->w.rope_cos != nullptr);
+    // norm1 + QKV projection: A = shifted copy left by the previous block's down GEMM (or by the embedding stage)
+    GemmParams p = ln_consumer(e, M, 3 * D, L.c1_qkv, L.b_qkv, e->qkv, 3 * D, e->stats[0], 1);
+    if (tc) p.f16_from = attention_qk_f16(T) ? 0 : 2 * D;
+    if (int rc = launch_gemm(e->hb, D, (const __nv_bfloat16*)L.w_qkv, D, p, tc ? EPI_BIAS_BF16_VF16 : EPI_BIAS_BF16, s,
+                             PROF_QKV_GEMM)) return rc;
+    if (tc) {
+        if (int rc = launch_attention_tc(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n, T,
+                                         c.prefix_tokens, c.heads, s)) return rc;
+    } else if (int rc = launch_attention(e->qkv, e->xn, (const float*)e->w.rope_cos, (const float*)e->w.rope_sin, n, T,
+                                         c.prefix_tokens, c.heads, s)) return rc;
+    // output projection: plain TMA add-reduction into the fp32 residual stream
+    p = GemmParams{};
+    p.M = M; p.N = D; p.K = D; p.bias = (const float*)L.b_o; p.out = e->h; p.ldo = D;
+    if (int rc = launch_gemm(e->xn, D, (const __nv_bfloat16*)L.w_o, D, p, EPI_RESID_F32, s, PROF_PROJ_GEMM)) return rc;
+    // norm2 as a kernel (unit gamma / zero beta: both are folded into W_up), leaving the statistics row of h
+    if (int rc = launch_layernorm<__nv_bfloat16>(e->h, 1, e->ones, e->zeros, e->hb, M, D, c.ln_eps, s, PROF_LAYERNORM,
+                                                 e->stats[1])) return rc;
+    p = GemmParams{};
+    p.M = M; p.N = I; p.K = D; p.bias = (const float*)L.b_up; p.out = e->u; p.ldo = I;
+    if (int rc = launch_gemm(e->hb, D, (const __nv_bfloat16*)L.w_up, D, p, EPI_BIAS_GELU_BF16, s, PROF_UP_GEMM)) return rc;
+    // down projection + residual; leaves hb / statistics for the next block's norm1
+    p = ln_producer(e, M, I, L.b_down, D, e->stats[1], 1, e->stats[0], 1, e->hb, D);
+    return launch_gemm(e->u, I, (const __nv_bfloat16*)L.w_down, I, p, EPI_RESID_LN_F32, s, PROF_DOWN_GEMM);
+}
+
 int encoder_layer(cbas_encoder* e, int li, int n, cudaStream_t s) {
     if (!e->ln_fused) return encoder_layer_unfused(e, li, n, s, false);
+    if (e->ln_fused == 2) return encoder_layer_hybrid(e, li, n, s);
     const cbas_encoder_cfg& c = e->cfg;
     const cbas_layer_weights& L = e->layers[li];
     const int D = c.hidden, I = c.intermediate, M = n * e->T;
@@ -723,7 +760,10 @@ int cbas_b200_encoder_set_option(cbas_encoder* enc, int32_t option, int32_t valu
             return 0;
         case CBAS_OPT_PRUNE_LAST_LAYER: enc->prune_last_layer = value != 0; return 0;
         case CBAS_OPT_RESIZE_KERNEL: enc->resize_tiled = value < 0 ? 0 : (value > 2 ? 2 : value); return 0;
-        case CBAS_OPT_LN_FUSION: enc->ln_fused = value != 0; return 0;
+        case CBAS_OPT_LN_FUSION:
+            if (value < 0 || value > 2) return fail("LayerNorm fusion must be 0 (standalone), 1 (both norms fused) or 2 (norm1 fused)");
+            enc->ln_fused = value;
+            return 0;
         case CBAS_OPT_SERPENTINE: enc->serpentine = value != 0; return 0;
     }
     return fail("unknown encoder option " + std::to_string(option));

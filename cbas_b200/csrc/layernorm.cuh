@@ -12,7 +12,8 @@ namespace cbas {
 template <int D, typename OutT>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ in, long long in_row_stride, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, OutT* __restrict__ out, int rows, float eps, int reverse) {
+                 const float* __restrict__ beta, OutT* __restrict__ out, int rows, float eps, int reverse,
+                 float* __restrict__ stats) {
     static_assert(D % 128 == 0, "D must be a multiple of 128");
     constexpr int V = D / 128;  // float4 per lane
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -35,7 +36,15 @@ layernorm_kernel(const float* __restrict__ in, long long in_row_stride, const fl
         x[i].x -= mean; x[i].y -= mean; x[i].z -= mean; x[i].w -= mean;
         q += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
     }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q * (1.0f / D) + eps);
+    if (stats) {
+        // hybrid LayerNorm fusion (encoder.cu): the statistics row a LayerNorm-producer GEMM expects of the stream it
+        // is about to update - shift = this row's exact mean, sum y = 0, sum y^2 = q  (LN_STAT_FLOATS = 36 floats)
+        float* srow = stats + (long long)warp * 36;
+        srow[lane] = lane == 16 ? q : 0.f;
+        if (lane < 4) srow[32 + lane] = lane == 0 ? mean : 0.f;
+    }
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll

@@ -103,6 +103,7 @@ void cbas_b200_encoder_destroy(cbas_encoder* enc);
 #define CBAS_OPT_RESIZE_KERNEL 2    /* PROCESSOR mode: 2 (default) = column-per-thread kernel when the geometry allows,
                                        1 = general shared-memory tiled kernel, 0 = per-pixel kernel                 */
 #define CBAS_OPT_LN_FUSION 3        /* 1 = norm1 / norm2 fused into the GEMMs around them (csrc/gemm_tcgen05.cuh),
+                                       2 = norm1 only (down GEMM -> next block's QKV GEMM), norm2 stays a kernel,
                                        0 = standalone LayerNorm kernels between the GEMMs (one HBM pass each)       */
 #define CBAS_OPT_SERPENTINE 4       /* standalone-LayerNorm path: 1 (default) = consecutive kernels of a block walk the rows
                                        in opposite directions (each starts on what its predecessor left in L2), 0 = all

@@ -180,7 +180,7 @@ def test_against_reference_encode_file_fixture(golden_dir):
     assert cos >= 0.999 and rel <= 2e-2 and nn_ok
 
 
-@pytest.mark.parametrize("ln_fusion", [0, 1], ids=["standalone_layernorm", "fused_layernorm"])
+@pytest.mark.parametrize("ln_fusion", [0, 1, 2], ids=["standalone_layernorm", "fused_layernorm", "norm1_fused"])
 def test_rows_whose_mean_dwarfs_their_spread(ln_fusion):
     """Every token row sits at a mean of ~40 with a spread of ~1 (embedding bias and prefix tokens shifted), and every
     residual update moves the row mean again (o_proj / down_proj biases shifted).  The standalone LayerNorm kernels
@@ -220,15 +220,16 @@ def test_fused_layernorm_matches_standalone_layernorm(arch, side, n):
     from cbas_b200 import _lib
     enc = DinoEncoder(f"synthetic:{arch}@4", "cuda", max_frames=24)
     frames = torch.from_numpy(oenc.synthetic_frames(n, side, side, seed=13)).cuda()
-    enc.set_option(_lib.OPT_LN_FUSION, 1)
-    fused = enc.encode_u8(frames)
-    taps_f = enc.debug_hidden(frames, 2)
     enc.set_option(_lib.OPT_LN_FUSION, 0)
     plain = enc.encode_u8(frames)
     taps_p = enc.debug_hidden(frames, 2)
-    print(f"[parity] fused vs standalone LayerNorm {arch}@{side}: embeddings {rel_err(fused, plain):.3e}, "
-          f"residual stream after 2 blocks {rel_err(taps_f, taps_p):.3e}")
-    assert rel_err(taps_f, taps_p) < 6e-3 and rel_err(fused, plain) < 8e-3
+    for mode, what in ((1, "norm1 + norm2 fused"), (2, "norm1 fused (the default)")):
+        enc.set_option(_lib.OPT_LN_FUSION, mode)
+        fused = enc.encode_u8(frames)
+        taps_f = enc.debug_hidden(frames, 2)
+        print(f"[parity] {what} vs standalone LayerNorm {arch}@{side}: embeddings {rel_err(fused, plain):.3e}, "
+              f"residual stream after 2 blocks {rel_err(taps_f, taps_p):.3e}")
+        assert rel_err(taps_f, taps_p) < 6e-3 and rel_err(fused, plain) < 8e-3
 
 
 @pytest.mark.parametrize("arch,side", [("vitb16", 224), ("vits16", 256), ("vitl16", 64)])
