@@ -46,6 +46,9 @@ constexpr int ATC_TRACE_SLOTS = 24;
 #ifndef ATC_POLY_PAIRS
 #define ATC_POLY_PAIRS 2  // of the 8 probability pairs per 16 columns, how many are exponentiated on the FMA pipe
 #endif
+#ifndef ATC_DIRECT_STORE
+#define ATC_DIRECT_STORE 0  // 1: the epilogue writes O straight to global memory (64 B per thread) instead of staging a TMA store
+#endif
 constexpr int ATC_XCHG_BYTES = 2 * 2 * 2 * 128 * 4;  // [max|sum][tile][half][row] floats
 constexpr int ATC_O_COL = 192;
 
@@ -180,8 +183,12 @@ __device__ __forceinline__ float2 ex2_poly3_pair(float2 x) {
 // while the current one is worked on.  Returns the partial row sum.
 // NP threads share a row; thread `part` publishes its partial max at xmax0 + 512 * part (shared-space address of a
 // [NP][128] float array, already offset to this row) and the NP warps of the lane quarter meet at named barrier bar_id.
+// `turn` (may be null): mbarrier to pass, at parity `turn_parity`, between the max pass and the exponential pass - the
+// two query tiles of an item take turns on the MUFU-heavy pass only; the max pass (TMEM loads and FMNMX) of one tile runs
+// under the other tile's exponentials.
 template <int TK, int CB, int CE, int NP>
-__device__ __forceinline__ float atc_softmax_range(uint32_t t_row, int T, float c, uint32_t xmax0, int part, int bar_id) {
+__device__ __forceinline__ float atc_softmax_range(uint32_t t_row, int T, float c, uint32_t xmax0, int part, int bar_id,
+                                                   uint64_t* turn, uint32_t turn_parity) {
     constexpr int W = CE - CB;
     constexpr bool kEdge = CE == TK;  // the last 16 columns of this share may lie past the frame
     float mx = -INFINITY;
@@ -218,6 +225,7 @@ __device__ __forceinline__ float atc_softmax_range(uint32_t t_row, int T, float 
     named_bar_sync(bar_id, 32 * NP);  // only the partner warps: same rows, the other shares of the keys
 #pragma unroll
     for (int q = 0; q < NP; ++q) mx = fmaxf(mx, ld_shared_f32(xmax0 + 512 * q));
+    if (turn) mbar_wait(turn, turn_parity);
     float sum = 0.f;
     if constexpr (W > 0) {
         constexpr int NC = W / 16;
@@ -512,8 +520,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             // and stores then always fall into the other tile's exponentials instead of both tiles queueing for the
             // MUFU at the same time and idling together afterwards.  (No phase can be skipped: a tile cannot complete
             // its next P hand-over before every warp of the other tile has seen this one.)
-            if (mt == 1) mbar_wait(&p_full[0], it & 1);
-            else if (it > 0) mbar_wait(&p_full[1], (it - 1) & 1);
+            // (The turn is taken between the two passes of the softmax: the max pass needs no MUFU.)
+            uint64_t* turn = mt == 1 ? &p_full[0] : (it > 0 ? &p_full[1] : nullptr);
+            const uint32_t turn_parity = mt == 1 ? (it & 1) : ((it - 1) & 1);
             mbar_wait(&s_full[mt], it & 1);
             tc_fence_after();
             if (stamper) ATC_STAMP(sbase);
@@ -521,10 +530,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
             if (warp_has_rows) {  // the partner warp (same rows) takes the same branch
                 const int bar_id = 1 + mt * 4 + quarter;
                 const uint32_t xmax0 = smem_u32(xchg + ((0 * 2 + mt) * 2 + 0) * 128 + rit);
-                if (half == 0) sum = atc_softmax_range<TK, 0, CA, 2>(t_row, T, c, xmax0, 0, bar_id);
-                else sum = atc_softmax_range<TK, CA, TK, 2>(t_row, T, c, xmax0, 1, bar_id);
+                if (half == 0) sum = atc_softmax_range<TK, 0, CA, 2>(t_row, T, c, xmax0, 0, bar_id, turn, turn_parity);
+                else sum = atc_softmax_range<TK, CA, TK, 2>(t_row, T, c, xmax0, 1, bar_id, turn, turn_parity);
+            } else if (turn) {
+                mbar_wait(turn, turn_parity);
             }
             *my_sum = sum;  // read by the partner thread after o_full (ordered through the mbarrier chain)
+            // The previous item's TMA store must have finished reading the staging rows before ANY warp of this tile
+            // rewrites them; every warp's next staging follows o_full(it), hence P V(it), hence this hand-over - so the
+            // storing thread checks here, thousands of cycles after it issued the store, instead of stalling its warp
+            // (and with it the whole tile's next softmax) right after the issue.
+            if ((warp & 7) == 0 && it > 0) {
+                if (elect_one()) tma_wait_group_read<0>();
+                __syncwarp();
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[mt]);
@@ -554,15 +573,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                     q.y = pack_bf16(__uint_as_float(v0[j + 2]) * inv_sum, __uint_as_float(v0[j + 3]) * inv_sum);
                     q.z = pack_bf16(__uint_as_float(v0[j + 4]) * inv_sum, __uint_as_float(v0[j + 5]) * inv_sum);
                     q.w = pack_bf16(__uint_as_float(v0[j + 6]) * inv_sum, __uint_as_float(v0[j + 7]) * inv_sum);
+#if ATC_DIRECT_STORE
+                    if (row < T)
+                        reinterpret_cast<uint4*>(p.out + ((long long)f * T + row) * p.D + h * 64 + half * 32)[j >> 3] = q;
+#else
                     if (row < T) *reinterpret_cast<uint4*>(srow + (((half * 4 + (j >> 3)) ^ (rit & 7)) << 4)) = q;
+#endif
                 }
             } else {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&o_empty[mt]);
             }
-            // one coalesced TMA store per query tile.  The staging rows are rewritten only in the next item's epilogue,
-            // which this thread's tile reaches through the max-exchange barrier, i.e. after the wait below.
+#if !ATC_DIRECT_STORE
+            // one coalesced TMA store per query tile
             fence_proxy_async();
             if (threadIdx.x == 0) ATC_STAMP(19);
             named_bar_sync(9 + mt, 256);
@@ -571,11 +595,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 12
                 if (elect_one()) {
                     if (mt) tma_store_3d(&tmap_o1, ostage + 16384, h * 64, 128, f);
                     else tma_store_3d(&tmap_o, ostage, h * 64, 0, f);
-                    tma_commit_group();
-                    tma_wait_group_read<0>();
+                    tma_commit_group();  // read-completion is checked before the next hand-over (see above)
                 }
                 __syncwarp();
             }
+#endif
             if (stamper) ATC_STAMP(sbase + 4);
         }
         if ((warp & 7) == 0 && elect_one()) tma_wait_group<0>();  // this CTA's output stores have landed
