@@ -254,6 +254,20 @@ def test_large_batch_uses_cta_pair_gemms():
     assert rel_err(big, small) < 1e-5
 
 
+def test_serpentine_row_order_changes_nothing():
+    """CBAS_OPT_SERPENTINE only changes the ORDER in which a kernel walks its row blocks (so that it starts on what its
+    predecessor left in L2): every row's arithmetic is the same, so the embeddings must be bitwise equal.  24 frames of
+    ViT-S/16 at 224 px = 4 824 rows: CTA-pair GEMMs, several row blocks per kernel, both attention tiles."""
+    from cbas_b200 import _lib
+    enc = DinoEncoder("synthetic:vits16@6", "cuda", max_frames=24)
+    frames = torch.from_numpy(oenc.synthetic_frames(24, 224, 224, seed=21)).cuda()
+    enc.set_option(_lib.OPT_SERPENTINE, 1)
+    on = enc.encode_u8(frames).clone()
+    enc.set_option(_lib.OPT_SERPENTINE, 0)
+    off = enc.encode_u8(frames).clone()
+    assert torch.equal(on, off)
+
+
 def test_batch_independence_and_chunking():
     enc = DinoEncoder("synthetic:vits16@3", "cuda", max_frames=4)
     frames = torch.from_numpy(oenc.synthetic_frames(10, 64, 64, seed=8)).cuda()
