@@ -55,7 +55,7 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p
     // the opt-in is a per-DEVICE attribute: one flag per instantiation and device ordinal
     static DeviceSmemOptIn optin;
     CBAS_CHECK(optin.ensure(kern, Cfg::kSmemBytes));
-    CUtensorMap tout = ta;  // unused by the direct-store (patch) epilogue
+    CUtensorMap tout;
     if (gemm_epi_ln_producer(EPI)) {
         if (!p.ln_in || !p.ln_out || !p.hb) return fail("LayerNorm-producer GEMM needs statistics in/out and the bf16 copy");
         if (4 * (p.N / BLOCK_N) > LN_STAT_SLOTS) return fail("LayerNorm-producer GEMM: N too wide for the statistics slots");
@@ -65,11 +65,16 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p
         if (!p.ln_c1 || !p.bias) return fail("LayerNorm-consumer GEMM needs c1 and c2");
         if (reinterpret_cast<uintptr_t>(p.ln_in) & 15) return fail("LayerNorm statistics must be 16-byte aligned");
     }
-    if (gemm_epi_staged(EPI)) {
+    {
         const bool f32 = !gemm_epi_out_bf16(EPI);
         if ((reinterpret_cast<uintptr_t>(p.out) & 15) || (p.ldo % (f32 ? 4 : 8)))
             return fail("GEMM output must be 16-byte aligned with a 16-byte multiple row pitch");
-        if (int rc = make_tmap(&tout, p.out, f32, p.M, p.N, p.ldo, gemm_slab_cols(EPI), GEMM_BLOCK_M)) return rc;
+        if (EPI == EPI_PATCH_F32) {
+            if (p.rows_in <= 0 || p.rows_out < p.rows_in + p.prefix) return fail("patch GEMM: bad row mapping");
+            tout = ta;  // unused: the patch epilogue copies its staged slabs out with plain stores (rows are re-mapped)
+        } else if (int rc = make_tmap(&tout, p.out, f32, p.M, p.N, p.ldo, gemm_slab_cols(EPI), GEMM_BLOCK_M)) {
+            return rc;
+        }
     }
     const int m_blocks = (p.M + GEMM_BLOCK_M * CG - 1) / (GEMM_BLOCK_M * CG);
     const int tiles = m_blocks * (p.N / BLOCK_N);

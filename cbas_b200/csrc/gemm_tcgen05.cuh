@@ -104,7 +104,7 @@ constexpr int GEMM_SLAB_BYTES = GEMM_BLOCK_M * 128;  // 128 rows x 128 B
 __host__ __device__ constexpr bool gemm_epi_out_bf16(int epi) {
     return epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_BF16_VF16;
 }
-__host__ __device__ constexpr bool gemm_epi_staged(int epi) { return epi != EPI_PATCH_F32; }  // LN producers included
+__host__ __device__ constexpr bool gemm_epi_staged(int) { return true; }  // every epilogue leaves through a staged TMA store
 __host__ __device__ constexpr bool gemm_epi_double_stage(int epi) { return epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_GELU_F32; }
 __host__ __device__ constexpr int gemm_slab_cols(int epi) { return gemm_epi_out_bf16(epi) ? 64 : 32; }
 // LayerNorm producer: per epilogue group one or two fp32 slabs (old h in by TMA, new h out, in place); the shifted
@@ -585,7 +585,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                     fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
                     named_bar_sync(1 + group, 256);
-                    if (issuer_warp) {
+                    if constexpr (EPI == EPI_PATCH_F32) {
+                        // Patch rows sit behind each frame's prefix tokens, so a 128-row slab is not one box of the output
+                        // (and TMA stores take no negative start coordinate to clip its head).  The group's 256 threads copy
+                        // the slab out themselves, eight lanes per row: every store instruction writes four whole 128-byte
+                        // lines, where the row-per-thread stores this replaces wrote 32 half sectors and were LSU-bound.
+                        const int ns = n_blk * BLOCK_N + s * kSlabCols;
+                        const int tl = (ew & 7) * 32 + lane;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int idx = tl + 256 * i, r = idx >> 3, c = idx & 7;
+                            const int m = m_base + r;
+                            if (m < p.M) {
+                                const int f = m / p.rows_in;
+                                const long long orow = (long long)f * p.rows_out + p.prefix + (m - f * p.rows_in);
+                                const float4 v = *reinterpret_cast<const float4*>(slab + r * 128 + ((c ^ (r & 7)) << 4));
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + ns + c * 4) = v;
+                            }
+                        }
+                        // (the barrier at the top of the group's next slab orders these reads before the slab is rewritten)
+                    } else if (issuer_warp) {
                         const int ns = n_blk * BLOCK_N + s * kSlabCols;
                         if (elect_one()) {
                             if (EPI == EPI_RESID_F32) tma_reduce_add_2d(&tmap_out, slab, ns, m_base);
@@ -593,37 +612,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             tma_commit_group();
                         }
                     }
-                }
-            } else {
-                // direct row-per-thread stores (patch-embedding rows are re-mapped, 0.7 % of the step)
-                constexpr int kColsPerWarp = BLOCK_N / 4;
-                const int col0 = (group * 2 + sub) * kColsPerWarp;
-                const int row = m_base + row_in_tile;
-                const bool row_ok = row < p.M;
-                const int f = row / p.rows_in;
-                const long long out_row = (long long)f * p.rows_out + p.prefix + (row - f * p.rows_in);
-#pragma unroll 1
-                for (int c = 0; c < kColsPerWarp; c += 16) {
-                    uint32_t v[16];
-                    tmem_ld_32x16(taddr_row + col0 + c, v);
-                    tmem_ld_wait();
-                    const int n0 = n_blk * BLOCK_N + col0 + c;
-                    if (row_ok) {
-                        float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-                            *reinterpret_cast<float4*>(o + j) =
-                                make_float4(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y,
-                                            __uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w);
-                        }
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (CG == 1) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_cluster(&tmem_empty[acc], 0);
                 }
             }
         }
