@@ -57,7 +57,9 @@ class StreamedEncoder:
         self.s_out = torch.cuda.Stream(device=dev)
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]
         self.ev_comp = [torch.cuda.Event() for _ in range(depth)]
-        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        # the host thread WAITS on these (once per chunk): blocking events put it to sleep instead of spinning on a core -
+        # with one process per GPU and two or three host threads each, eight ranks otherwise fight over a 16-core host
+        self.ev_out = [torch.cuda.Event(blocking=True) for _ in range(depth)]
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
