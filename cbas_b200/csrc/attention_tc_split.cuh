@@ -366,6 +366,13 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
                     tmem_st_wait();
                 }
                 sums[(pp * 2 + half) * 128 + rit] = sum;  // read by the merging threads after o_full (mbarrier chain)
+                // the previous tile's TMA store must have read its staging rows before they are rewritten (one item
+                // later); every rewrite follows a later o_full[1], hence this hand-over: the storing thread checks here,
+                // long after the issue, instead of stalling its warp behind the store (attention_tc.cuh does the same)
+                if (warp == 8 && g > 0) {
+                    if (elect_one()) tma_wait_group_read<0>();
+                    __syncwarp();
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[pp]);
@@ -415,8 +422,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
                         *reinterpret_cast<uint4*>(srow + (((4 * half + j) ^ (rit & 7)) << 4)) =
                             make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                 }
-                // one TMA store per query tile; the staging rows of tile qt are rewritten one item later, after this
-                // thread has passed the barrier again, i.e. after the wait on the store's shared-memory read
+                // one TMA store per query tile; the staging rows of tile qt are rewritten one item later
                 fence_proxy_async();
                 named_bar_sync(9, 256);
                 if (warp == 8) {
@@ -424,7 +430,6 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box 
                         if (qt == nq - 1) tma_store_3d(&tmap_o1, ostage + qt * 16384, h * 64, qt * 128, f);
                         else tma_store_3d(&tmap_o, ostage + qt * 16384, h * 64, qt * 128, f);
                         tma_commit_group();
-                        tma_wait_group_read<0>();
                     }
                     __syncwarp();
                 }
