@@ -6,8 +6,8 @@
 // and runs ~40 small launches per batch.  Here the per-frame work is hoisted out of the windows and the window stages
 // run over chunks of up to 37 888 windows (two waves of 128-window tiles on 148 SMs; 7 launches per chunk):
 //
-//   H1 head_split_embed   f16 embeddings -> exact bf16 hi/lo split [n, 2F]; per-frame lin1 logits q = W1 x (fp32)
-//   H2 tcgen05 GEMM       P[n,384] = x (Wc|Wd|Wa)^T   - EMA, deltas and lin1 are linear, so the three 768->128
+//   H1 head_split_embed   f16 embeddings -> exact bf16 hi/lo split [n, 2F]
+//   H2 tcgen05 GEMM       P[n,512] = x (Wc|Wd|Wa|W1|0)^T   - EMA, deltas and lin1 are linear, so the three 768->128
 //                         bottleneck projections are taken ONCE per frame and the EMA / delta / acceleration
 //                         recurrences run in the 128-d projected space (verified identity)
 //   H3 head_features      per window: window-local EMA (alpha), reflect-padded delta / delta-delta, +bias, GELU,
@@ -48,6 +48,7 @@ using namespace cbas;
 namespace {
 
 constexpr int HEAD_BN = 128;    // bottleneck width
+constexpr int HEAD_PW = 512;    // per-frame projection row: cls | delta | acc bottlenecks (384), lin1 logits (C <= 32), zero padding
 constexpr int HEAD_LIN0 = 256;  // lin0 width = LSTM input width
 constexpr int HEAD_MAX_HS = 128; // LSTM hidden size: 64 (default) or 128 (the reference's sweep, sweep_runner.py:106)
 constexpr int HEAD_MAX_C = 32;
@@ -65,51 +66,44 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 }
 
 // ---------------------------------------------------------------------------------------------- H1
-// one warp per frame.  x' = [hi | lo] (2F bf16; the GEMM re-reads hi for its third K block, GemmParams::a_wrap);  q[f][c] = sum_k lin1_w[c][k] x[k]
+// x' = [hi | lo] (2F bf16; the GEMM re-reads hi for its third K block, GemmParams::a_wrap).  Eight elements per thread:
+// 16-byte loads and stores, HBM-bound (2 or 4 bytes in, 4 bytes out per element).
 template <typename InT>  // __half: the stored `cls` rows (split exact); float: forward(x) windows (16-bit split)
 __global__ void __launch_bounds__(256)
-head_split_embed_kernel(const InT* __restrict__ emb, long long n, int F, __nv_bfloat16* __restrict__ xs,
-                        const float* __restrict__ lin1_w, int C, float* __restrict__ q) {
-    const long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (f >= n) return;
-    const InT* x = emb + f * F;
-    __nv_bfloat16* o = xs + f * 2 * F;
-    float acc[HEAD_MAX_C];
+head_split_embed_kernel(const InT* __restrict__ emb, long long n, int F, __nv_bfloat16* __restrict__ xs) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one group of 8 elements
+    const int g8 = F >> 3;
+    if (i >= n * g8) return;
+    const long long f = i / g8;
+    const int k = (int)(i - f * g8) << 3;
+    float v[8];
+    if constexpr (sizeof(InT) == 2) {
+        const uint4 q = __ldcs(reinterpret_cast<const uint4*>(emb + f * F + k));
+        const __half2* h2 = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
-    for (int c = 0; c < HEAD_MAX_C; ++c) acc[c] = 0.f;
-    for (int k = lane * 2; k < F; k += 64) {
-        float2 v;
-        if constexpr (sizeof(InT) == 2) v = __half22float2(*reinterpret_cast<const __half2*>(x + k));
-        else v = *reinterpret_cast<const float2*>(x + k);
+        for (int j = 0; j < 4; ++j) { const float2 t = __half22float2(h2[j]); v[2 * j] = t.x; v[2 * j + 1] = t.y; }
+    } else {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(emb + f * F + k));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(emb + f * F + k + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
         __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v.x, h0, l0);
-        split_bf16(v.y, h1, l1);
-        __nv_bfloat162 hi, lo;
-        hi.x = h0; hi.y = h1; lo.x = l0; lo.y = l1;
-        *reinterpret_cast<__nv_bfloat162*>(o + k) = hi;
-        *reinterpret_cast<__nv_bfloat162*>(o + F + k) = lo;
-#pragma unroll
-        for (int c = 0; c < HEAD_MAX_C; ++c) {
-            if (c < C) {
-                const float2 w = __ldg(reinterpret_cast<const float2*>(lin1_w + (long long)c * F + k));
-                acc[c] = fmaf(w.x, v.x, fmaf(w.y, v.y, acc[c]));
-            }
-        }
+        split_bf16(v[2 * j], h0, l0);
+        split_bf16(v[2 * j + 1], h1, l1);
+        hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
     }
-#pragma unroll
-    for (int c = 0; c < HEAD_MAX_C; ++c) {
-        if (c < C) {
-            const float s = warp_sum(acc[c]);
-            if (lane == 0) q[f * C + c] = s;
-        }
-    }
+    __nv_bfloat16* o = xs + f * 2 * F + k;
+    *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(o + F) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // ---------------------------------------------------------------------------------------------- H3
 struct FeatParams {
-    const float* P;      // [n, 384] per-frame projections (cls | delta | acc), no bias
-    const float* q;      // [n, C] per-frame lin1 projections, no bias
+    const float* P;      // [n, HEAD_PW] per-frame projections (cls | delta | acc | lin1 logits | zeros), no bias
     long long n;         // frames in the video
     long long w0;        // centre frame of the first window of this chunk
     long long stride;    // centre-frame distance between consecutive windows: 1 (infer_file) or T (forward(x))
@@ -169,14 +163,14 @@ head_features_kernel(const FeatParams p) {
     };
     auto load3 = [&](int t, float (&c)[4], float (&d)[4], float (&e)[4], float& qq) {
         const long long g = frame_of(t);
-        const float* pr = p.P + g * 384 + lane * 4;
+        const float* pr = p.P + g * HEAD_PW + lane * 4;
         const float4 x0 = __ldg(reinterpret_cast<const float4*>(pr));
         const float4 x1 = __ldg(reinterpret_cast<const float4*>(pr + 128));
         const float4 x2 = __ldg(reinterpret_cast<const float4*>(pr + 256));
         c[0] = x0.x; c[1] = x0.y; c[2] = x0.z; c[3] = x0.w;
         d[0] = x1.x; d[1] = x1.y; d[2] = x1.z; d[3] = x1.w;
         e[0] = x2.x; e[1] = x2.y; e[2] = x2.z; e[3] = x2.w;
-        qq = lane < p.C ? __ldg(p.q + g * p.C + lane) : 0.f;
+        qq = lane < p.C ? __ldg(p.P + g * HEAD_PW + 3 * HEAD_BN + lane) : 0.f;  // lin1 logits ride in the same row
     };
 
     // EMA states of the three projected streams at t = 0, 1, 2 (the reflect padding needs s1, s2 for t = 0)
@@ -626,7 +620,7 @@ struct cbas_head {
     int device = 0;  // the CUDA device that was current at create time: every entry point runs there
     int l = 0, r = 0;
     // derived device weights
-    __nv_bfloat16* wp = nullptr;    // [384, 3F]
+    __nv_bfloat16* wp = nullptr;    // [HEAD_PW, 3F]: cls | delta | acc bottleneck rows, lin1 rows, zero rows
     __nv_bfloat16* w0 = nullptr;    // [256, 1152]
     // per LSTM layer: input-gate weights of both directions [8Hs, 3*K_in] (K_in = 256, then 2Hs), b_ih + b_hh [8Hs],
     // recurrent weights [2][Hs k][Hs unit][4 gate]
@@ -637,15 +631,14 @@ struct cbas_head {
     // and the recurrent weights are [2 dir][hi, lo][256 columns][64 k] bf16 (head_lstm_tc.cuh)
     __nv_bfloat16* whh_tc[2] = {nullptr, nullptr};
     float *b3 = nullptr, *ln_g = nullptr, *ln_b = nullptr, *b0 = nullptr;
-    float *lin1_w = nullptr, *lin1_b = nullptr, *lin2_w = nullptr, *lin2_b = nullptr, *att_w = nullptr;
+    float *lin1_b = nullptr, *lin2_w = nullptr, *lin2_b = nullptr, *att_w = nullptr;  // (lin1_w lives in wp)
     float att_b = 0.f, inv_att_temp = 1.f, gate_sig = 0.5f;
     // workspace
     long long cap_frames = 0;
     int max_chunk_windows = 2 * 148 * 128;  // windows per pass of the window stages: two waves of 128-window tiles
     int chunk_windows = 0;                  // ... the chunk workspace currently holds (grown on demand)
     __nv_bfloat16* xs = nullptr;  // [cap, 3F]
-    float* P = nullptr;           // [cap, 384]
-    float* q = nullptr;           // [cap, C]
+    float* P = nullptr;           // [cap, HEAD_PW]
     __nv_bfloat16* A = nullptr;   // [chunk*T, 1152]  (reused as Z' [chunk*T, 768])
     float* Z = nullptr;           // [chunk*T, 256]
     float* G = nullptr;           // [chunk*T, 8Hs]
@@ -656,16 +649,15 @@ struct cbas_head {
 
 namespace {
 void head_free_ws(cbas_head* h) {
-    cudaFree(h->xs); cudaFree(h->P); cudaFree(h->q);
-    h->xs = nullptr; h->P = nullptr; h->q = nullptr; h->cap_frames = 0;
+    cudaFree(h->xs); cudaFree(h->P);
+    h->xs = nullptr; h->P = nullptr; h->cap_frames = 0;
 }
 int head_ensure_ws(cbas_head* h, long long n) {
     if (n <= h->cap_frames) return 0;
     head_free_ws(h);
     const int F = h->cfg.in_features, C = h->cfg.out_features;
     CBAS_CHECK(cudaMalloc((void**)&h->xs, (size_t)n * 2 * F * 2));
-    CBAS_CHECK(cudaMalloc((void**)&h->P, (size_t)n * 384 * 4));
-    CBAS_CHECK(cudaMalloc((void**)&h->q, (size_t)n * C * 4));
+    CBAS_CHECK(cudaMalloc((void**)&h->P, (size_t)n * HEAD_PW * 4));
     h->cap_frames = n;
     return 0;
 }
@@ -726,7 +718,16 @@ int cbas_b200_head_create(const cbas_head_cfg* cfg, const cbas_head_weights* w, 
     };
     std::vector<float> W;
     if (!rc) rc = cat3(w->cls_w, w->delta_w, w->acc_w, (size_t)HEAD_BN * F, W);
-    if (!rc) rc = upload_split_weight(W, 3 * HEAD_BN, F, &h->wp);
+    if (!rc) {
+        // rows 384 .. 384 + C - 1: lin1 (the linear branch's per-frame logits come out of the same GEMM), zero rows after
+        std::vector<float> l1;
+        rc = download(w->lin1_w, (size_t)C * F, l1);
+        if (!rc) {
+            W.insert(W.end(), l1.begin(), l1.end());
+            W.resize((size_t)HEAD_PW * F, 0.f);
+        }
+    }
+    if (!rc) rc = upload_split_weight(W, HEAD_PW, F, &h->wp);
     if (!rc) rc = cat3(w->cls_b, w->delta_b, w->acc_b, HEAD_BN, W);
     if (!rc) rc = upload_f32(W, &h->b3);
     if (!rc) rc = cat3(w->cls_ln_g, w->delta_ln_g, w->acc_ln_g, HEAD_BN, W);
@@ -813,8 +814,6 @@ int cbas_b200_head_create(const cbas_head_cfg* cfg, const cbas_head_weights* w, 
                                      "recurrent weight upload");
         }
     }
-    if (!rc) rc = download(w->lin1_w, (size_t)C * F, W);
-    if (!rc) rc = upload_f32(W, &h->lin1_w);
     if (!rc) rc = download(w->lin1_b, C, W);
     if (!rc) rc = upload_f32(W, &h->lin1_b);
     if (!rc) rc = download(w->lin2_w, (size_t)C * 2 * HS, W);
@@ -845,7 +844,7 @@ void cbas_b200_head_destroy(cbas_head* h) {
     head_free_ws(h);
     cudaFree(h->wp); cudaFree(h->w0); cudaFree(h->b3); cudaFree(h->ln_g); cudaFree(h->ln_b); cudaFree(h->b0);
     for (int i = 0; i < 2; ++i) { cudaFree(h->wih[i]); cudaFree(h->bg[i]); cudaFree(h->whh_t[i]); cudaFree(h->whh_tc[i]); }
-    cudaFree(h->H0); cudaFree(h->lin1_w); cudaFree(h->lin1_b);
+    cudaFree(h->H0); cudaFree(h->lin1_b);
     cudaFree(h->lin2_w); cudaFree(h->lin2_b); cudaFree(h->att_w);
     cudaFree(h->A); cudaFree(h->Z); cudaFree(h->G); cudaFree(h->H); cudaFree(h->lin);
     delete h;
@@ -859,19 +858,17 @@ static int head_run(cbas_head* h, const void* x_dev, bool x_is_f16, long long n_
     // H1 + H2: per-frame work, once for the whole sequence
     {
         ProfScope prof(PROF_HEAD_SPLIT, s);
-        const long long threads = n_frames * 32;
-        const unsigned grid = (unsigned)((threads + 255) / 256);
-        if (x_is_f16)
-            head_split_embed_kernel<__half><<<grid, 256, 0, s>>>((const __half*)x_dev, n_frames, F, h->xs, h->lin1_w, C, h->q);
-        else
-            head_split_embed_kernel<float><<<grid, 256, 0, s>>>((const float*)x_dev, n_frames, F, h->xs, h->lin1_w, C, h->q);
+        const long long groups = n_frames * (F / 8);
+        const unsigned grid = (unsigned)((groups + 255) / 256);
+        if (x_is_f16) head_split_embed_kernel<__half><<<grid, 256, 0, s>>>((const __half*)x_dev, n_frames, F, h->xs);
+        else head_split_embed_kernel<float><<<grid, 256, 0, s>>>((const float*)x_dev, n_frames, F, h->xs);
         count_launch();
         if (int rc = check_cuda(cudaGetLastError(), "head_split_embed_kernel launch")) return rc;
     }
     for (long long f0 = 0; f0 < n_frames; f0 += (1 << 20)) {  // the GEMM takes int M
         const int m = (int)((n_frames - f0) < (1 << 20) ? (n_frames - f0) : (1 << 20));
         GemmParams p{};
-        p.M = m; p.N = 3 * HEAD_BN; p.K = 3 * F; p.a_wrap = 2 * F; p.bias = nullptr; p.out = h->P + f0 * 384; p.ldo = 384;
+        p.M = m; p.N = HEAD_PW; p.K = 3 * F; p.a_wrap = 2 * F; p.bias = nullptr; p.out = h->P + f0 * HEAD_PW; p.ldo = HEAD_PW;
         if (int rc = launch_gemm(h->xs + f0 * 2 * F, 2 * F, h->wp, 3 * F, p, EPI_BIAS_F32, s, PROF_HEAD_PROJ_GEMM))
             return rc;
     }
@@ -884,7 +881,7 @@ static int head_run(cbas_head* h, const void* x_dev, bool x_is_f16, long long n_
         const int rows = nw * T;
         {
             ProfScope prof(PROF_HEAD_FEATURES, s);
-            FeatParams fp{h->P, h->q, n_frames, first_center + w0 * stride, stride, nw, T, T / 2, h->l, h->r,
+            FeatParams fp{h->P, n_frames, first_center + w0 * stride, stride, nw, T, T / 2, h->l, h->r,
                           h->cfg.ema_alpha, h->b3, h->ln_g, h->ln_b, h->lin1_b, C, h->A, h->lin};
             head_features_kernel<<<(nw * 32 + 255) / 256, 256, 0, s>>>(fp);
             count_launch();
