@@ -40,3 +40,15 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.EncoderWeights) == 13 * 8
     assert ctypes.sizeof(_lib.HeadCfg) == 9 * 4
     assert ctypes.sizeof(_lib.HeadWeights) == 28 * 8 + 8 + 8 * 8  # + the second LSTM layer
+
+
+def test_option_constants_match_header():
+    """The per-handle option numbers the Python mirror passes to cbas_b200_encoder_set_option are the header's."""
+    src = open(os.path.join(ROOT, "include", "cbas_b200.h")).read()
+    want = {k: int(v) for k, v in re.findall(r"#define\s+(CBAS_OPT_\w+)\s+(\d+)", src)}
+    assert want == {"CBAS_OPT_ATTENTION_IMPL": _lib.OPT_ATTENTION_IMPL, "CBAS_OPT_PRUNE_LAST_LAYER": _lib.OPT_PRUNE_LAST_LAYER,
+                    "CBAS_OPT_RESIZE_KERNEL": _lib.OPT_RESIZE_KERNEL, "CBAS_OPT_LN_FUSION": _lib.OPT_LN_FUSION,
+                    "CBAS_OPT_SERPENTINE": _lib.OPT_SERPENTINE}
+    lib = _lib.lib()
+    # validation of the option value happens before any CUDA call
+    assert lib.cbas_b200_encoder_set_option(None, _lib.OPT_LN_FUSION, 2) != 0 and b"null" in lib.cbas_b200_last_error()
